@@ -1,0 +1,152 @@
+/*
+ * gl_commit.h — C ABI of libgl_commit: the B200-native (sm_100a) replacement for the commitment hot path of the
+ * plonky2 prover that plonky2.5 drives (PolynomialBatch::from_values / from_coeffs, MerkleTree::new,
+ * fri_committed_trees).  This is the drop-in boundary: plain C, `uint64_t` Goldilocks words (little-endian,
+ * GoldilocksField is #[repr(transparent)] u64; inputs may be non-canonical, outputs are always canonical),
+ * integer status returns, no unwinding across the boundary, no torch types.
+ *
+ * The reference reaches this path only through (file:line under /root/reference):
+ *     src/p3/mod.rs:250   builder.build::<C>()  -> plonky2 circuit_builder.rs · build      -> from_values (commit #0)
+ *     src/p3/mod.rs:260   data.prove(pw)        -> plonky2 plonk/prover.rs                 -> from_values x2, from_coeffs,
+ *                                                  fri/oracle.rs · prove_openings -> fri/prover.rs · fri_committed_trees
+ * (and the 23 other prove/verify pairs listed in SURVEY.md §4).  The upstream functions live in the un-vendored crate
+ * plonky2 @ 3de92d9ed1721cec133e4e1e1b3ec7facb756ccf (Cargo.toml:15-19); each entry point below names the upstream
+ * item it replaces.  The Rust binding a maintainer would add is shown in INTEGRATION.md / ffi/rust/.
+ *
+ * Threading: every call takes the context's mutex; calls on one context are serialised, distinct contexts are
+ * independent (one context per prover thread is the intended use under `cargo test`'s parallel tests).
+ * All calls are synchronous: on return the outputs are visible to the host.
+ * There is NO CPU fallback: without a CUDA device gl_ctx_create fails with GL_ERR_CUDA.
+ */
+#ifndef GL_COMMIT_H
+#define GL_COMMIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gl_ctx gl_ctx;
+typedef uint64_t gl_handle; /* device-resident object id (tree / batch / fri state); 0 is never valid */
+
+enum {
+    GL_OK = 0,
+    GL_ERR_INVALID = -1,     /* argument violates an upstream assert (message via gl_ctx_last_error)            */
+    GL_ERR_CUDA = -2,        /* CUDA runtime error / no device                                                   */
+    GL_ERR_OOM = -3,         /* device or host allocation failed                                                 */
+    GL_ERR_HANDLE = -4,      /* unknown handle                                                                   */
+    GL_ERR_UNSUPPORTED = -5  /* shape outside what the kernels support (e.g. log_n + rate_bits > 32)             */
+};
+
+#define GL_ABI_VERSION 1
+int gl_abi_version(void);
+const char* gl_strerror(int code);
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int gl_ctx_create(gl_ctx** out, int device);
+void gl_ctx_destroy(gl_ctx* ctx);
+const char* gl_ctx_last_error(gl_ctx* ctx);
+/* the CUDA stream all work of this context is enqueued on (cudaStream_t as integer) — for event timing */
+uint64_t gl_ctx_stream(gl_ctx* ctx);
+
+/* ---- PolynomialBatch::from_values / from_coeffs  (plonky2 fri/oracle.rs) ------------------------------------
+ * cols          n_cols host pointers, each 2^log_n words: Vec<PolynomialValues<F>> (input_is_coeffs = 0) or
+ *               Vec<PolynomialCoeffs<F>> (input_is_coeffs = 1) without a copy.  blinding is always false here.
+ * out_coeffs    n_cols * N words, column-major, canonical (PolynomialBatch::polynomials); NULL = do not copy back
+ * out_leaves    R * n_cols words row-major, row i = LDE point index bitrev(i) (MerkleTree::leaves); NULL = keep on device
+ * out_digests   2*(R - 2^cap_height)*4 words, plonky2 interleaved layout (MerkleTree::digests); NULL = keep on device
+ * out_cap       2^cap_height * 4 words (MerkleTree::cap), always written
+ * out_batch     if non-NULL receives a handle to the device-resident batch (free with gl_tree_free); if NULL the
+ *               device copy is released before returning.
+ * Errors mirror upstream asserts: cap_height > log2(R) -> GL_ERR_INVALID ("cap_height should be at most
+ * log2(leaves.len())"); n_cols == 0 -> GL_ERR_INVALID.
+ */
+int gl_commit(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+              uint32_t cap_height, int input_is_coeffs, uint64_t* out_coeffs, uint64_t* out_leaves,
+              uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_batch);
+
+/* ---- MerkleTree::new  (plonky2 hash/merkle_tree.rs) ---------------------------------------------------------
+ * leaves: n_leaves rows of leaf_len words, packed row-major on the host.  n_leaves must be a power of two. */
+int gl_merkle_new(gl_ctx* ctx, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t cap_height,
+                  uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_tree);
+
+/* ---- device-resident trees / batches: MerkleTree::get, MerkleTree::prove, PolynomialBatch::get_lde_values ---- */
+typedef struct {
+    uint64_t n_leaves;    /* R */
+    uint32_t leaf_len;    /* n_cols */
+    uint32_t cap_height;
+    uint32_t degree_log;  /* log_n   (0 for bare trees) */
+    uint32_t rate_bits;   /*         (0 for bare trees) */
+    uint32_t has_coeffs;
+    uint32_t pitch;       /* device row pitch in words */
+} gl_tree_info_t;
+int gl_tree_info(gl_ctx* ctx, gl_handle tree, gl_tree_info_t* out);
+int gl_tree_get(gl_ctx* ctx, gl_handle tree, uint64_t leaf_index, uint64_t* out_row /* leaf_len */);
+/* siblings bottom-up, (log2(n_leaves) - cap_height) * 4 words — MerkleProof::siblings */
+int gl_tree_prove(gl_ctx* ctx, gl_handle tree, uint64_t leaf_index, uint64_t* out_siblings);
+/* leaves[bitrev(index * step)] — PolynomialBatch::get_lde_values */
+int gl_tree_get_lde_values(gl_ctx* ctx, gl_handle tree, uint64_t index, uint64_t step, uint64_t* out_row);
+enum { GL_PART_COEFFS = 0, GL_PART_LEAVES = 1, GL_PART_DIGESTS = 2, GL_PART_CAP = 3 };
+/* bulk device -> host copy of one part, same layouts as gl_commit's outputs */
+int gl_tree_read(gl_ctx* ctx, gl_handle tree, int part, uint64_t* out);
+int gl_tree_free(gl_ctx* ctx, gl_handle tree);
+
+/* ---- FRI commit phase: fri_committed_trees  (plonky2 fri/prover.rs) ------------------------------------------
+ * The Fiat–Shamir challenger stays on the host (upstream code, untouched); per layer the host calls
+ *     gl_fri_commit_layer -> observes the cap, draws beta -> gl_fri_fold(beta)
+ * coeffs / values: `len` extension elements each, interleaved [a0, a1]; values = coset_fft(coeffs, shift 7) in
+ * natural order, exactly the two arguments upstream passes.                                                     */
+int gl_fri_begin(gl_ctx* ctx, const uint64_t* coeffs_ext, const uint64_t* values_ext, uint64_t len,
+                 uint32_t rate_bits, uint32_t cap_height, gl_handle* out_fri);
+/* reverse_index_bits_in_place(values); leaves = chunks(2^arity_bits).flatten(); MerkleTree::new(leaves, cap_height) */
+int gl_fri_commit_layer(gl_ctx* ctx, gl_handle fri, uint32_t arity_bits, uint64_t* out_leaves, uint64_t* out_digests,
+                        uint64_t* out_cap, gl_handle* out_tree);
+/* coeffs <- reduce_with_powers over chunks; shift <- shift^arity; values <- coset_fft(coeffs, shift) */
+int gl_fri_fold(gl_ctx* ctx, gl_handle fri, const uint64_t beta[2]);
+/* coeffs truncated to len >> rate_bits (final_poly); out_len in extension elements */
+int gl_fri_final_poly(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* out_len);
+int gl_fri_end(gl_ctx* ctx, gl_handle fri);
+
+/* ---- Poseidon permutation batch (plonky2 hash/poseidon.rs · PoseidonPermutation::permute) ---------------------
+ * states: n x 12 words, permuted in place, canonical on return.  Used by the host-side Challenger mirror.       */
+int gl_poseidon_permute(gl_ctx* ctx, uint64_t* states, uint64_t n);
+
+/* ---- device-pointer stage API (inputs/outputs already in HBM; multi-GPU host code and benchmarks) ------------- */
+/* whole commit from a device-resident column-major matrix d_cols[n_cols][2^log_n] (col_stride words apart) */
+int gl_dev_commit(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
+                  uint32_t rate_bits, uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_batch);
+/* stage 1 of the sharded commit: iNTT + coset LDE of a column shard; d_out_rows = [R][out_pitch] row-major
+ * (out_pitch multiple of 8), rows in bit-reversed LDE order; d_out_coeffs = [N][out_pitch] or NULL              */
+int gl_dev_lde(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
+               uint32_t rate_bits, int input_is_coeffs, uint64_t* d_out_rows, uint32_t out_pitch,
+               uint64_t* d_out_coeffs);
+/* copy a received [n_rows][src_cols] block into columns [dst_col_off, dst_col_off+src_cols) of [n_rows][dst_pitch] */
+int gl_dev_repack(gl_ctx* ctx, const uint64_t* d_src, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,
+                  uint32_t dst_pitch, uint32_t dst_col_off);
+/* stage 3: Merkle subtrees over device rows [n_leaves][pitch]; d_digests 2*(n_leaves-2^cap_height)*4 words (device),
+ * out_cap host 2^cap_height*4 */
+int gl_dev_merkle(gl_ctx* ctx, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch,
+                  uint32_t cap_height, uint64_t* d_digests, uint64_t* out_cap);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------------- */
+enum {
+    GL_STAGE_H2D = 0, GL_STAGE_TRANSPOSE = 1, GL_STAGE_INTT = 2, GL_STAGE_LDE = 3, GL_STAGE_LEAF_HASH = 4,
+    GL_STAGE_TREE = 5, GL_STAGE_D2H = 6, GL_N_STAGES = 7
+};
+/* CUDA-event milliseconds of the stages of the last gl_commit / gl_dev_commit on this context (timed on the
+ * context's stream); kernel launch counts of that call in out_launches[GL_N_STAGES] (may be NULL). */
+int gl_ctx_stage_times(gl_ctx* ctx, float* out_ms, uint32_t* out_launches);
+/* integer-pipe calibration (K7): runs `iters` dependent-chain iterations of {0: IMAD.WIDE.U32, 1: IADD3, 2: mixed,
+ * 3: Goldilocks modmul, 4: Poseidon permutation} on every SM, returns operations per second in *out_ops_per_s */
+int gl_microbench(gl_ctx* ctx, int which, uint32_t iters, double* out_ops_per_s);
+
+/* pinned host memory for benchmarks / shims that want fast PCIe copies */
+void* gl_host_alloc(size_t bytes);
+void gl_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GL_COMMIT_H */

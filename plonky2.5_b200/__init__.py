@@ -1,0 +1,14 @@
+"""plonky2.5_b200 — B200-native (sm_100a) commitment engine for the plonky2 prover that plonky2.5 drives.
+
+Scope: exactly the hot path of SURVEY.md §8 — PolynomialBatch::from_values / from_coeffs (iNTT, coset LDE,
+bit-reversed row-major leaves), Poseidon MerkleTree::new, FRI commit-phase folding — behind the C ABI of
+include/gl_commit.h.  The directory name contains a dot, so import it as ``plonky25_b200`` (the shim module at the
+repository root) or via importlib.
+"""
+from . import _lib  # noqa: F401
+from .api import (Challenger, Context, FriParams, GlError, MerkleCap, MerkleTree, PolynomialBatch,  # noqa: F401
+                  default_context, fri_committed_trees)
+from .build import build  # noqa: F401
+
+__all__ = ["Challenger", "Context", "FriParams", "GlError", "MerkleCap", "MerkleTree", "PolynomialBatch",
+           "default_context", "fri_committed_trees", "build"]

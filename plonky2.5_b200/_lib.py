@@ -1,0 +1,77 @@
+"""ctypes binding of libgl_commit.so — exactly the C ABI in include/gl_commit.h, nothing else.
+
+There is no fallback: if the CUDA library is missing or no device is present, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgl_commit.so")
+
+GL_OK, GL_ERR_INVALID, GL_ERR_CUDA, GL_ERR_OOM, GL_ERR_HANDLE, GL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+GL_PART_COEFFS, GL_PART_LEAVES, GL_PART_DIGESTS, GL_PART_CAP = 0, 1, 2, 3
+STAGES = ("h2d", "transpose", "intt", "lde", "leaf_hash", "tree", "d2h")
+
+
+class TreeInfo(ctypes.Structure):
+    _fields_ = [("n_leaves", c_uint64), ("leaf_len", c_uint32), ("cap_height", c_uint32), ("degree_log", c_uint32),
+                ("rate_bits", c_uint32), ("has_coeffs", c_uint32), ("pitch", c_uint32)]
+
+
+u64p = POINTER(c_uint64)
+
+# name -> (restype, argtypes); every symbol include/gl_commit.h declares
+SIGNATURES = {
+    "gl_abi_version": (c_int, []),
+    "gl_strerror": (c_char_p, [c_int]),
+    "gl_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
+    "gl_ctx_destroy": (None, [c_void_p]),
+    "gl_ctx_last_error": (c_char_p, [c_void_p]),
+    "gl_ctx_stream": (c_uint64, [c_void_p]),
+    "gl_commit": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_uint32, c_int,
+                          c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "gl_merkle_new": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "gl_tree_info": (c_int, [c_void_p, c_uint64, POINTER(TreeInfo)]),
+    "gl_tree_get": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p]),
+    "gl_tree_prove": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p]),
+    "gl_tree_get_lde_values": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_void_p]),
+    "gl_tree_read": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
+    "gl_tree_free": (c_int, [c_void_p, c_uint64]),
+    "gl_fri_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, POINTER(c_uint64)]),
+    "gl_fri_commit_layer": (c_int, [c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "gl_fri_fold": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "gl_fri_final_poly": (c_int, [c_void_p, c_uint64, c_void_p, POINTER(c_uint64)]),
+    "gl_fri_end": (c_int, [c_void_p, c_uint64]),
+    "gl_poseidon_permute": (c_int, [c_void_p, c_void_p, c_uint64]),
+    "gl_dev_commit": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_int, c_void_p,
+                              POINTER(c_uint64)]),
+    "gl_dev_lde": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_int, c_void_p, c_uint32, c_void_p]),
+    "gl_dev_repack": (c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_void_p, c_uint32, c_uint32]),
+    "gl_dev_merkle": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]),
+    "gl_ctx_stage_times": (c_int, [c_void_p, POINTER(c_float), POINTER(c_uint32)]),
+    "gl_microbench": (c_int, [c_void_p, c_int, c_uint32, POINTER(c_double)]),
+    "gl_host_alloc": (c_void_p, [c_size_t]),
+    "gl_host_free": (None, [c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and bind every symbol.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python plonky2.5_b200/build.py` "
+                           "(there is no CPU fallback for the commitment path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the ABI and the header drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,357 @@
+"""Host-side mirror of the plonky2 operator interface for the commitment hot path, on top of the C ABI.
+
+The reference's toolchain (Rust) is absent from this image, so the host layer above ``include/gl_commit.h`` is
+written in Python with the SAME names, argument meaning and error behaviour as the upstream items the reference
+drives from /root/reference/src/p3/mod.rs:250 (``builder.build``) and :260 (``data.prove``):
+
+    plonky2 fri/oracle.rs        PolynomialBatch::from_values / from_coeffs / get_lde_values
+    plonky2 hash/merkle_tree.rs  MerkleTree::new / get / prove,  MerkleCap
+    plonky2 fri/prover.rs        fri_committed_trees
+    plonky2 iop/challenger.rs    Challenger (observe_* / get_challenge / get_extension_challenge)
+
+Upstream ``assert!`` panics become ``ValueError`` (GL_ERR_INVALID) here.  Field elements are ``numpy.uint64``;
+outputs are canonical.  All compute happens in libgl_commit.so on the GPU — there is no CPU path in this module.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_uint64, c_void_p
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+P = 0xFFFF_FFFF_0000_0001
+SPONGE_RATE = 8
+SPONGE_WIDTH = 12
+
+
+class GlError(RuntimeError):
+    pass
+
+
+def _check(ctx: "Context", rc: int):
+    if rc == _lib.GL_OK:
+        return
+    msg = ctx.lib.gl_ctx_last_error(ctx.handle).decode() if ctx.handle else ""
+    text = f"{ctx.lib.gl_strerror(rc).decode()}: {msg}"
+    if rc == _lib.GL_ERR_INVALID:
+        raise ValueError(text)
+    if rc == _lib.GL_ERR_OOM:
+        raise MemoryError(text)
+    raise GlError(text)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+class Context:
+    """One CUDA device + stream + cached twiddle tables (gl_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.handle = c_void_p()
+        rc = self.lib.gl_ctx_create(byref(self.handle), device)
+        if rc != _lib.GL_OK:
+            self.handle = None
+            raise GlError(f"gl_ctx_create(device={device}) failed: {self.lib.gl_strerror(rc).decode()} "
+                          "(libgl_commit has no CPU fallback; a CUDA device is required)")
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.gl_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.gl_ctx_stream(self.handle))
+
+    def stage_times(self) -> Tuple[dict, dict]:
+        ms = (ctypes.c_float * len(_lib.STAGES))()
+        ln = (ctypes.c_uint32 * len(_lib.STAGES))()
+        _check(self, self.lib.gl_ctx_stage_times(self.handle, ms, ln))
+        return dict(zip(_lib.STAGES, map(float, ms))), dict(zip(_lib.STAGES, map(int, ln)))
+
+    def microbench(self, which: int, iters: int = 2000) -> float:
+        out = ctypes.c_double()
+        _check(self, self.lib.gl_microbench(self.handle, which, iters, byref(out)))
+        return out.value
+
+    def poseidon_permute(self, states: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, SPONGE_WIDTH).copy()
+        _check(self, self.lib.gl_poseidon_permute(self.handle, _ptr(s), s.shape[0]))
+        return s
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class MerkleCap:
+    def __init__(self, hashes: np.ndarray):
+        self.hashes = hashes.reshape(-1, 4)
+
+    def height(self) -> int:
+        return int(self.hashes.shape[0]).bit_length() - 1
+
+    def flatten(self) -> np.ndarray:
+        return self.hashes.reshape(-1)
+
+    def __len__(self):
+        return self.hashes.shape[0]
+
+
+class MerkleTree:
+    """plonky2 hash/merkle_tree.rs · MerkleTree { leaves, digests, cap } — device resident, host views on demand."""
+
+    def __init__(self, ctx: Context, handle: int, cap: np.ndarray, leaves=None, digests=None):
+        self.ctx = ctx
+        self._h = handle
+        self.cap = MerkleCap(cap)
+        info = _lib.TreeInfo()
+        _check(ctx, ctx.lib.gl_tree_info(ctx.handle, handle, byref(info)))
+        self.n_leaves, self.leaf_len, self.cap_height = int(info.n_leaves), int(info.leaf_len), int(info.cap_height)
+        self.degree_log, self.rate_bits = int(info.degree_log), int(info.rate_bits)
+        self._leaves, self._digests = leaves, digests
+
+    @classmethod
+    def new(cls, leaves, cap_height: int, ctx: Optional[Context] = None, copy_back: bool = False) -> "MerkleTree":
+        ctx = ctx or default_context()
+        lv = np.ascontiguousarray(leaves, dtype=np.uint64)
+        if lv.ndim != 2:
+            raise ValueError("leaves must be a 2-D array [n_leaves][leaf_len]")
+        n, ll = lv.shape
+        cap = np.zeros((1 << cap_height) * 4 if cap_height < 40 else 0, dtype=np.uint64)
+        dig = None
+        if copy_back and n >= (1 << cap_height):
+            dig = np.zeros((2 * (n - (1 << cap_height)), 4), dtype=np.uint64)
+        h = c_uint64()
+        _check(ctx, ctx.lib.gl_merkle_new(ctx.handle, _ptr(lv), n, ll, cap_height, _ptr(dig), _ptr(cap), byref(h)))
+        return cls(ctx, h.value, cap, leaves=lv if copy_back else None, digests=dig)
+
+    @property
+    def leaves(self) -> np.ndarray:
+        if self._leaves is None:
+            out = np.zeros((self.n_leaves, self.leaf_len), dtype=np.uint64)
+            _check(self.ctx, self.ctx.lib.gl_tree_read(self.ctx.handle, self._h, _lib.GL_PART_LEAVES, _ptr(out)))
+            self._leaves = out
+        return self._leaves
+
+    @property
+    def digests(self) -> np.ndarray:
+        if self._digests is None:
+            out = np.zeros((2 * (self.n_leaves - (1 << self.cap_height)), 4), dtype=np.uint64)
+            _check(self.ctx, self.ctx.lib.gl_tree_read(self.ctx.handle, self._h, _lib.GL_PART_DIGESTS, _ptr(out)))
+            self._digests = out
+        return self._digests
+
+    def get(self, i: int) -> np.ndarray:
+        out = np.zeros(self.leaf_len, dtype=np.uint64)
+        _check(self.ctx, self.ctx.lib.gl_tree_get(self.ctx.handle, self._h, i, _ptr(out)))
+        return out
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        """MerkleProof::siblings, bottom-up, shape [log2(n_leaves) - cap_height][4]."""
+        depth = self.n_leaves.bit_length() - 1 - self.cap_height
+        out = np.zeros((depth, 4), dtype=np.uint64)
+        _check(self.ctx, self.ctx.lib.gl_tree_prove(self.ctx.handle, self._h, leaf_index, _ptr(out)))
+        return out
+
+    def free(self):
+        if self._h and self.ctx.handle:
+            self.ctx.lib.gl_tree_free(self.ctx.handle, self._h)
+        self._h = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PolynomialBatch:
+    """plonky2 fri/oracle.rs · PolynomialBatch { polynomials, merkle_tree, degree_log, rate_bits, blinding }."""
+
+    def __init__(self, ctx, tree: MerkleTree, n_cols: int, polynomials=None):
+        self.ctx = ctx
+        self.merkle_tree = tree
+        self.degree_log = tree.degree_log
+        self.rate_bits = tree.rate_bits
+        self.blinding = False
+        self._n_cols = n_cols
+        self._polys = polynomials
+
+    @staticmethod
+    def _cols(values) -> Tuple[List[np.ndarray], int]:
+        cols = [np.ascontiguousarray(v, dtype=np.uint64) for v in values]
+        if not cols:
+            raise ValueError("empty polynomial batch")
+        n = cols[0].shape[0]
+        if any(c.ndim != 1 or c.shape[0] != n for c in cols):
+            raise ValueError("Polynomial degrees inconsistent")
+        if n == 0 or n & (n - 1):
+            raise ValueError("polynomial length must be a power of two")
+        return cols, n.bit_length() - 1
+
+    @classmethod
+    def _commit(cls, values, rate_bits, blinding, cap_height, is_coeffs, ctx, copy_back):
+        if blinding:
+            raise ValueError("blinding (zero_knowledge) is not on the GPU path: the reference runs with zk off "
+                             "(/root/reference/src/p3/mod.rs:231)")
+        ctx = ctx or default_context()
+        cols, log_n = cls._cols(values)
+        n_cols, n = len(cols), 1 << log_n
+        rows = n << rate_bits
+        ptrs = (c_void_p * n_cols)(*[c.ctypes.data for c in cols])
+        if cap_height > 40:
+            raise ValueError("cap_height should be at most log2(leaves.len())")
+        cap = np.zeros(4 << cap_height, dtype=np.uint64)
+        oc = ol = od = None
+        if copy_back:
+            oc = np.zeros((n_cols, n), dtype=np.uint64)
+            ol = np.zeros((rows, n_cols), dtype=np.uint64)
+            od = np.zeros((max(2 * (rows - (1 << cap_height)), 0), 4), dtype=np.uint64)
+        h = c_uint64()
+        _check(ctx, ctx.lib.gl_commit(ctx.handle, ptrs, n_cols, log_n, rate_bits, cap_height, int(is_coeffs),
+                                      _ptr(oc), _ptr(ol), _ptr(od), _ptr(cap), byref(h)))
+        tree = MerkleTree(ctx, h.value, cap, leaves=ol, digests=od)
+        return cls(ctx, tree, n_cols, polynomials=oc)
+
+    @classmethod
+    def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None, fft_root_table=None,
+                    ctx: Optional[Context] = None, copy_back: bool = False) -> "PolynomialBatch":
+        """values: Vec<PolynomialValues<F>> — sequence of equal-length 1-D uint64 arrays (one per column)."""
+        return cls._commit(values, rate_bits, blinding, cap_height, False, ctx, copy_back)
+
+    @classmethod
+    def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None, fft_root_table=None,
+                    ctx: Optional[Context] = None, copy_back: bool = False) -> "PolynomialBatch":
+        return cls._commit(polynomials, rate_bits, blinding, cap_height, True, ctx, copy_back)
+
+    @property
+    def polynomials(self) -> np.ndarray:
+        """[n_cols][N] canonical coefficients."""
+        if self._polys is None:
+            out = np.zeros((self._n_cols, 1 << self.degree_log), dtype=np.uint64)
+            t = self.merkle_tree
+            _check(self.ctx, self.ctx.lib.gl_tree_read(self.ctx.handle, t._h, _lib.GL_PART_COEFFS, _ptr(out)))
+            self._polys = out
+        return self._polys
+
+    def get_lde_values(self, index: int, step: int) -> np.ndarray:
+        t = self.merkle_tree
+        out = np.zeros(t.leaf_len, dtype=np.uint64)
+        _check(self.ctx, self.ctx.lib.gl_tree_get_lde_values(self.ctx.handle, t._h, index, step, _ptr(out)))
+        return out
+
+
+class Challenger:
+    """plonky2 iop/challenger.rs · Challenger<F, PoseidonHash>: duplex sponge; the permutation runs on the GPU."""
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.sponge_state = np.zeros(SPONGE_WIDTH, dtype=np.uint64)
+        self.input_buffer: List[int] = []
+        self.output_buffer: List[int] = []
+
+    def observe_element(self, e: int):
+        self.output_buffer = []
+        self.input_buffer.append(int(e) % P)
+        if len(self.input_buffer) == SPONGE_RATE:
+            self._duplexing()
+
+    def observe_elements(self, es):
+        for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist():
+            self.observe_element(e)
+
+    def observe_hash(self, h):
+        self.observe_elements(h)
+
+    def observe_cap(self, cap):
+        self.observe_elements(cap.flatten() if isinstance(cap, MerkleCap) else cap)
+
+    def observe_extension_element(self, e):
+        self.observe_elements(e)
+
+    def observe_extension_elements(self, es):
+        self.observe_elements(es)
+
+    def get_challenge(self) -> int:
+        if self.input_buffer or not self.output_buffer:
+            self._duplexing()
+        return self.output_buffer.pop()
+
+    def get_extension_challenge(self) -> Tuple[int, int]:
+        c0 = self.get_challenge()
+        c1 = self.get_challenge()
+        return (c0, c1)
+
+    def _duplexing(self):
+        for i, v in enumerate(self.input_buffer):
+            self.sponge_state[i] = v
+        self.input_buffer = []
+        self.sponge_state = self.ctx.poseidon_permute(self.sponge_state)[0]
+        self.output_buffer = [int(x) for x in self.sponge_state[:SPONGE_RATE]]
+
+
+class FriParams:
+    """The fields of plonky2 fri/mod.rs · FriParams that fri_committed_trees reads."""
+
+    def __init__(self, rate_bits: int, cap_height: int, reduction_arity_bits: Sequence[int]):
+        self.rate_bits = rate_bits
+        self.cap_height = cap_height
+        self.reduction_arity_bits = list(reduction_arity_bits)
+
+
+def fri_committed_trees(polynomial_coeffs, polynomial_values, challenger, fri_params: FriParams,
+                        ctx: Optional[Context] = None):
+    """plonky2 fri/prover.rs · fri_committed_trees.
+
+    polynomial_coeffs / polynomial_values: [len][2] extension elements (values = coset_fft(coeffs, 7), natural order).
+    `challenger` is the caller's Fiat–Shamir transcript (any object with observe_cap / get_extension_challenge /
+    observe_extension_elements).  Returns (trees, final_poly_coeffs[len_final][2]).
+    """
+    ctx = ctx or default_context()
+    co = np.ascontiguousarray(polynomial_coeffs, dtype=np.uint64).reshape(-1, 2)
+    va = np.ascontiguousarray(polynomial_values, dtype=np.uint64).reshape(-1, 2)
+    if co.shape != va.shape:
+        raise ValueError("coeffs and values must have the same length")
+    lib = ctx.lib
+    fh = c_uint64()
+    _check(ctx, lib.gl_fri_begin(ctx.handle, _ptr(co), _ptr(va), co.shape[0], fri_params.rate_bits, fri_params.cap_height,
+                                 byref(fh)))
+    trees = []
+    try:
+        for arity_bits in fri_params.reduction_arity_bits:
+            cap = np.zeros(4 << fri_params.cap_height, dtype=np.uint64)
+            th = c_uint64()
+            _check(ctx, lib.gl_fri_commit_layer(ctx.handle, fh.value, arity_bits, None, None, _ptr(cap), byref(th)))
+            tree = MerkleTree(ctx, th.value, cap)
+            challenger.observe_cap(tree.cap.flatten())
+            trees.append(tree)
+            beta = challenger.get_extension_challenge()
+            b = np.array([int(beta[0]), int(beta[1])], dtype=np.uint64)
+            _check(ctx, lib.gl_fri_fold(ctx.handle, fh.value, _ptr(b)))
+        n = c_uint64()
+        _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh.value, None, byref(n)))
+        final = np.zeros((n.value, 2), dtype=np.uint64)
+        _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh.value, _ptr(final), byref(n)))
+        challenger.observe_extension_elements(final)
+    finally:
+        lib.gl_fri_end(ctx.handle, fh.value)
+    return trees, final

@@ -1,0 +1,812 @@
+// libgl_commit: context, stage orchestration and the extern "C" boundary declared in include/gl_commit.h.
+//
+// Host-side mirror of plonky2 fri/oracle.rs · PolynomialBatch::from_values / from_coeffs, hash/merkle_tree.rs ·
+// MerkleTree::new and fri/prover.rs · fri_committed_trees (driven from /root/reference/src/p3/mod.rs:250,260).
+// Everything here is plumbing around the kernels in ntt.cuh / merkle.cuh / fri.cuh; there is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gl_commit.h"
+#include "fri.cuh"
+#include "merkle.cuh"
+#include "microbench.cuh"
+#include "ntt.cuh"
+
+namespace {
+
+struct GlError {
+    int code;
+    std::string msg;
+};
+
+#define GL_THROW(code, ...)                              \
+    do {                                                 \
+        char _b[512];                                    \
+        snprintf(_b, sizeof _b, __VA_ARGS__);            \
+        throw GlError{code, _b};                         \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            int _c = (_e == cudaErrorMemoryAllocation) ? GL_ERR_OOM : GL_ERR_CUDA;                         \
+            GL_THROW(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+        }                                                                                                  \
+    } while (0)
+
+struct DevBuf {
+    uint64_t* p = nullptr;
+    size_t words = 0;
+    void ensure(size_t w) {
+        if (w <= words) return;
+        release();
+        CUDA_CHECK(cudaMalloc(&p, (w ? w : 1) * sizeof(uint64_t)));
+        words = w;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        words = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+inline uint32_t log2_exact(uint64_t n) {
+    uint32_t l = 0;
+    while ((1ULL << l) < n) l++;
+    return l;
+}
+inline uint32_t h_bitrev(uint32_t x, uint32_t bits) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+// how the log_n stages are split into shared-memory passes (each <= 10 stages, as even as possible)
+std::vector<uint32_t> plan_passes(uint32_t n) {
+    std::vector<uint32_t> v;
+    if (n < 3) return v;
+    uint32_t k = (n + 9) / 10, base = n / k, rem = n % k;
+    for (uint32_t i = 0; i < k; i++) v.push_back(base + (i < rem ? 1 : 0));
+    return v;
+}
+
+struct CosetTable {   // pre-scale factors g^j split as g^(l << (n - a1)) * g^(o_lo) for the first pass
+    uint64_t g = 1;
+    DevBuf A, B;
+};
+
+struct Tree {
+    uint64_t n_leaves = 0;
+    uint32_t leaf_len = 0, pitch = 0, cap_height = 0, degree_log = 0, rate_bits = 0;
+    DevBuf leaves, digests, coeffs, d_cap;
+    bool has_coeffs = false;
+    std::vector<uint64_t> cap;
+};
+
+struct Fri {
+    uint64_t len = 0;
+    uint32_t rate_bits = 0, cap_height = 0;
+    uint64_t shift = gl::COSET_SHIFT;
+    uint32_t last_arity_bits = 0;
+    DevBuf coeffs, values, tmp;   // values are kept in bit-reversed order (what the next layer's leaves need)
+};
+
+}  // namespace
+
+struct gl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::map<uint32_t, std::unique_ptr<DevBuf>> roots;                       // log_n -> W
+    std::map<uint64_t, std::unique_ptr<std::vector<CosetTable>>> lde_tables;  // (log_n, rate_bits) -> per coset
+    DevBuf in_stage, vals, scratch;
+    std::map<gl_handle, std::unique_ptr<Tree>> trees;
+    std::map<gl_handle, std::unique_ptr<Fri>> fris;
+    gl_handle next_handle = 1;
+    cudaEvent_t ev[GL_N_STAGES + 1] = {};
+    float stage_ms[GL_N_STAGES] = {};
+    uint32_t launches[GL_N_STAGES] = {};
+    int sm_count = 148;
+};
+
+namespace {
+
+const uint64_t* get_roots(gl_ctx* c, uint32_t log_n) {
+    auto it = c->roots.find(log_n);
+    if (it != c->roots.end()) return it->second->p;
+    size_t half = log_n ? (size_t)1 << (log_n - 1) : 1;
+    std::vector<uint64_t> w(half);
+    uint64_t root = gl::h_root_of_unity(log_n), cur = 1;
+    for (size_t e = 0; e < half; e++) { w[e] = cur; cur = gl::h_mul(cur, root); }
+    auto buf = std::make_unique<DevBuf>();
+    buf->ensure(half);
+    CUDA_CHECK(cudaMemcpyAsync(buf->p, w.data(), half * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const uint64_t* p = buf->p;
+    c->roots[log_n] = std::move(buf);
+    return p;
+}
+
+void fill_coset_table(gl_ctx* c, CosetTable& t, uint64_t g, uint32_t log_n) {
+    t.g = g;
+    auto passes = plan_passes(log_n);
+    if (passes.empty()) return;
+    uint32_t a1 = passes[0], b = log_n - a1;
+    std::vector<uint64_t> A((size_t)1 << a1), B((size_t)1 << b);
+    uint64_t gb = gl::h_pow(g, 1ULL << b), cur = 1;
+    for (auto& x : A) { x = cur; cur = gl::h_mul(cur, gb); }
+    cur = 1;
+    for (auto& x : B) { x = cur; cur = gl::h_mul(cur, g); }
+    t.A.ensure(A.size());
+    t.B.ensure(B.size());
+    CUDA_CHECK(cudaMemcpyAsync(t.A.p, A.data(), A.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(t.B.p, B.data(), B.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// coset s of the LDE evaluates at 7 * w_R^s * w_N^m
+const std::vector<CosetTable>& get_lde_tables(gl_ctx* c, uint32_t log_n, uint32_t rate_bits) {
+    uint64_t key = ((uint64_t)log_n << 32) | rate_bits;
+    auto it = c->lde_tables.find(key);
+    if (it != c->lde_tables.end()) return *it->second;
+    auto v = std::make_unique<std::vector<CosetTable>>((size_t)1 << rate_bits);
+    uint64_t wR = gl::h_root_of_unity(log_n + rate_bits), g = gl::COSET_SHIFT;
+    for (uint32_t s = 0; s < (1u << rate_bits); s++) {
+        fill_coset_table(c, (*v)[s], g, log_n);
+        g = gl::h_mul(g, wR);
+    }
+    auto& ref = *v;
+    c->lde_tables[key] = std::move(v);
+    return ref;
+}
+
+template <int G>
+void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* launches) {
+    p.ncg = cols_padded / G;
+    uint32_t T = 1u << p.a;
+    uint32_t threads = T * G / 8;
+    size_t smem = ((size_t)(T + (T >> 3)) * G + (T >> 1)) * 8;
+    uint64_t grid = (uint64_t)p.ncg << (p.log_n - p.a);
+    if (grid >= (1ULL << 31)) GL_THROW(GL_ERR_UNSUPPORTED, "NTT grid too large");
+    ntt::ntt_pass_kernel<G><<<(uint32_t)grid, threads, smem, c->stream>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+    if (launches) (*launches)++;
+}
+
+// Batched NTT of `cols_padded` columns (multiple of G) of a row-major matrix.
+//   forward (ifft=false): src -> dst in in-place-DIF order (row p = X[bitrev(p)]), optional coset pre-scale `pre`;
+//                         later passes run in place on dst.
+//   ifft:                 all passes but the last run IN PLACE ON src (destroyed); last pass stores to dst in natural
+//                         coefficient order scaled by 1/N.
+void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32_t dst_pitch, uint32_t cols_padded,
+             uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches) {
+    const uint64_t* W = get_roots(c, log_n);
+    uint64_t n_inv = ifft ? gl::h_inv(((uint64_t)1 << log_n) % gl::P) : 1;
+    auto passes = plan_passes(log_n);
+    if (passes.empty()) {
+        dim3 grid((cols_padded + 63) / 64, 1u << log_n);
+        ntt::ntt_tiny_kernel<<<grid, 64, 0, c->stream>>>(src, dst, src_pitch, dst_pitch, cols_padded, log_n,
+                                                         gl::h_root_of_unity(log_n), pre ? pre->g : 1, ifft ? 1 : 0, n_inv);
+        CUDA_CHECK(cudaGetLastError());
+        if (launches) (*launches)++;
+        return;
+    }
+    uint32_t log_blk = log_n;
+    for (size_t i = 0; i < passes.size(); i++) {
+        bool first = i == 0, last = i + 1 == passes.size();
+        ntt::PassParams p{};
+        p.log_n = log_n;
+        p.log_blk = log_blk;
+        p.a = passes[i];
+        p.W = W;
+        p.preA = (first && pre) ? pre->A.p : nullptr;
+        p.preB = (first && pre) ? pre->B.p : nullptr;
+        p.store_mode = (ifft && last) ? 1 : 0;
+        p.scale = (ifft && last) ? n_inv : 1;
+        if (ifft) {
+            p.src = src; p.src_pitch = src_pitch;
+            p.dst = last ? dst : src; p.dst_pitch = last ? dst_pitch : src_pitch;
+        } else {
+            p.src = first ? src : dst; p.src_pitch = first ? src_pitch : dst_pitch;
+            p.dst = dst; p.dst_pitch = dst_pitch;
+        }
+        int g = G;
+        if (g == 8 && p.a == 10) g = 4;   // keep 512 threads / 40 KB shared memory per CTA
+        switch (g) {
+            case 8: launch_pass<8>(c, p, cols_padded, launches); break;
+            case 4: launch_pass<4>(c, p, cols_padded, launches); break;
+            case 2: launch_pass<2>(c, p, cols_padded, launches); break;
+            default: GL_THROW(GL_ERR_INVALID, "bad column group");
+        }
+        log_blk -= passes[i];
+    }
+}
+
+void merkle_build(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch,
+                  uint32_t cap_height, uint64_t* d_digests, uint64_t* d_cap, uint32_t* leaf_launches,
+                  uint32_t* tree_launches, cudaEvent_t after_leaves) {
+    uint32_t log_leaves = log2_exact(n_leaves);
+    uint32_t log_sub = log_leaves - cap_height;
+    constexpr int LB = 128;
+    merkle::leaf_hash_kernel<LB><<<(uint32_t)((n_leaves + LB - 1) / LB), LB, 0, c->stream>>>(
+        d_leaves, pitch, leaf_len, n_leaves, log_sub, d_digests, d_cap);
+    CUDA_CHECK(cudaGetLastError());
+    if (leaf_launches) (*leaf_launches)++;
+    if (after_leaves) CUDA_CHECK(cudaEventRecord(after_leaves, c->stream));
+    for (uint32_t layer = 1; layer <= log_sub; layer++) {
+        uint64_t n_nodes = n_leaves >> layer;
+        constexpr int TB = 128;
+        merkle::tree_level_kernel<TB><<<(uint32_t)((n_nodes + TB - 1) / TB), TB, 0, c->stream>>>(d_digests, d_cap, layer,
+                                                                                               log_sub, n_nodes);
+        CUDA_CHECK(cudaGetLastError());
+        if (tree_launches) (*tree_launches)++;
+    }
+}
+
+void check_shape(uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height) {
+    if (n_cols == 0) GL_THROW(GL_ERR_INVALID, "empty polynomial batch");
+    if (log_n + rate_bits > 31) GL_THROW(GL_ERR_UNSUPPORTED, "log_n + rate_bits = %u > 31", log_n + rate_bits);
+    if (cap_height > log_n + rate_bits)
+        GL_THROW(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len()) (cap_height=%u, log2(leaves)=%u)",
+                 cap_height, log_n + rate_bits);
+}
+
+gl_handle put_tree(gl_ctx* c, std::unique_ptr<Tree> t) {
+    gl_handle h = c->next_handle++;
+    c->trees[h] = std::move(t);
+    return h;
+}
+Tree* find_tree(gl_ctx* c, gl_handle h) {
+    auto it = c->trees.find(h);
+    if (it == c->trees.end()) GL_THROW(GL_ERR_HANDLE, "unknown tree handle %llu", (unsigned long long)h);
+    return it->second.get();
+}
+Fri* find_fri(gl_ctx* c, gl_handle h) {
+    auto it = c->fris.find(h);
+    if (it == c->fris.end()) GL_THROW(GL_ERR_HANDLE, "unknown fri handle %llu", (unsigned long long)h);
+    return it->second.get();
+}
+
+void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream)); }
+
+// iNTT + coset LDE of a device column-major matrix into row-major outputs (shared by gl_commit / gl_dev_*)
+void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+               int is_coeffs, uint64_t* d_coeffs, uint32_t coeff_pitch, uint64_t* d_rows, uint32_t row_pitch, bool timed) {
+    const uint64_t N = 1ULL << log_n;
+    const uint32_t cols_padded = round_up(n_cols, 8);
+    dim3 tb(32, 8);
+    dim3 tg((uint32_t)((N + 31) / 32), (coeff_pitch + 31) / 32);
+    uint32_t* l_tr = timed ? &c->launches[GL_STAGE_TRANSPOSE] : nullptr;
+    uint32_t* l_in = timed ? &c->launches[GL_STAGE_INTT] : nullptr;
+    uint32_t* l_ld = timed ? &c->launches[GL_STAGE_LDE] : nullptr;
+    if (is_coeffs) {
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, d_coeffs, coeff_pitch, n_cols, N);
+        CUDA_CHECK(cudaGetLastError());
+        if (l_tr) (*l_tr)++;
+        if (timed) { record(c, GL_STAGE_INTT); }
+    } else {
+        c->vals.ensure(N * coeff_pitch);
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, c->vals.p, coeff_pitch, n_cols, N);
+        CUDA_CHECK(cudaGetLastError());
+        if (l_tr) (*l_tr)++;
+        if (timed) record(c, GL_STAGE_INTT);
+        run_ntt(c, c->vals.p, coeff_pitch, d_coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, 8, l_in);
+    }
+    if (timed) record(c, GL_STAGE_LDE);
+    const auto& tabs = get_lde_tables(c, log_n, rate_bits);
+    for (uint32_t s = 0; s < (1u << rate_bits); s++) {
+        uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch;
+        run_ntt(c, d_coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], 8, l_ld);
+    }
+}
+
+int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_cols_in, uint64_t col_stride, uint32_t n_cols,
+                uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, int is_coeffs, uint64_t* out_coeffs,
+                uint64_t* out_leaves, uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_batch) {
+    check_shape(n_cols, log_n, rate_bits, cap_height);
+    if (!out_cap) GL_THROW(GL_ERR_INVALID, "out_cap is NULL");
+    const uint64_t N = 1ULL << log_n, R = N << rate_bits;
+    const uint32_t pitch = round_up(n_cols, 8);
+    const uint64_t n_dig = 2 * (R - (1ULL << cap_height));
+    // warm the tables before the timed region starts
+    get_roots(c, log_n);
+    get_lde_tables(c, log_n, rate_bits);
+    auto t = std::make_unique<Tree>();
+    t->n_leaves = R; t->leaf_len = n_cols; t->pitch = pitch; t->cap_height = cap_height;
+    t->degree_log = log_n; t->rate_bits = rate_bits; t->has_coeffs = true;
+    t->coeffs.ensure(N * pitch);
+    t->leaves.ensure(R * pitch);
+    t->digests.ensure(n_dig * 4);
+    t->d_cap.ensure(4ULL << cap_height);
+    t->cap.resize(4ULL << cap_height);
+    memset(c->launches, 0, sizeof c->launches);
+
+    record(c, GL_STAGE_H2D);
+    const uint64_t* d_cols = d_cols_in;
+    if (host_cols) {
+        c->in_stage.ensure(N * n_cols);
+        for (uint32_t j = 0; j < n_cols; j++) {
+            if (!host_cols[j]) GL_THROW(GL_ERR_INVALID, "cols[%u] is NULL", j);
+            CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, host_cols[j], N * 8, cudaMemcpyHostToDevice, c->stream));
+        }
+        d_cols = c->in_stage.p;
+        col_stride = N;
+    }
+    record(c, GL_STAGE_TRANSPOSE);
+    lde_stage(c, d_cols, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
+    record(c, GL_STAGE_LEAF_HASH);
+    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
+                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    record(c, GL_STAGE_D2H);
+    CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, (32ULL << cap_height), cudaMemcpyDeviceToHost, c->stream));
+    if (out_coeffs) {
+        // row-major [N][pitch] -> column-major [n_cols][N] on the device, then one contiguous copy
+        c->scratch.ensure(N * n_cols);
+        dim3 tb(32, 8), tg((uint32_t)((N + 31) / 32), (n_cols + 31) / 32);
+        ntt::transpose_out_kernel<<<tg, tb, 0, c->stream>>>(t->coeffs.p, pitch, c->scratch.p, N, n_cols, N);
+        CUDA_CHECK(cudaGetLastError());
+        c->launches[GL_STAGE_D2H]++;
+        CUDA_CHECK(cudaMemcpyAsync(out_coeffs, c->scratch.p, N * n_cols * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (out_leaves)
+        CUDA_CHECK(cudaMemcpy2DAsync(out_leaves, (size_t)n_cols * 8, t->leaves.p, (size_t)pitch * 8, (size_t)n_cols * 8, R,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    if (out_digests && n_dig)
+        CUDA_CHECK(cudaMemcpyAsync(out_digests, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));
+    record(c, GL_N_STAGES);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < GL_N_STAGES; i++) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    memcpy(out_cap, t->cap.data(), 32ULL << cap_height);
+    if (out_batch) *out_batch = put_tree(c, std::move(t));
+    return GL_OK;
+}
+
+}  // namespace
+
+// ============================================================================================ extern "C"
+#define GL_API_BEGIN(ctx)                        \
+    if (!(ctx)) return GL_ERR_INVALID;           \
+    std::lock_guard<std::mutex> _lk((ctx)->mu);  \
+    try {                                        \
+        CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define GL_API_END(ctx)                          \
+    }                                            \
+    catch (const GlError& e) {                   \
+        (ctx)->err = e.msg;                      \
+        cudaGetLastError();                      \
+        return e.code;                           \
+    }                                            \
+    catch (const std::bad_alloc&) {              \
+        (ctx)->err = "host allocation failed";   \
+        return GL_ERR_OOM;                       \
+    }                                            \
+    catch (...) {                                \
+        (ctx)->err = "unknown error";            \
+        return GL_ERR_CUDA;                      \
+    }
+
+extern "C" {
+
+int gl_abi_version(void) { return GL_ABI_VERSION; }
+
+const char* gl_strerror(int code) {
+    switch (code) {
+        case GL_OK: return "ok";
+        case GL_ERR_INVALID: return "invalid argument";
+        case GL_ERR_CUDA: return "CUDA error";
+        case GL_ERR_OOM: return "out of memory";
+        case GL_ERR_HANDLE: return "unknown handle";
+        case GL_ERR_UNSUPPORTED: return "unsupported shape";
+        default: return "unknown error code";
+    }
+}
+
+int gl_ctx_create(gl_ctx** out, int device) {
+    if (!out) return GL_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return GL_ERR_CUDA; }
+    if (device < 0 || device >= n) return GL_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return GL_ERR_CUDA;
+    gl_ctx* c = new (std::nothrow) gl_ctx;
+    if (!c) return GL_ERR_OOM;
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return GL_OK;
+}
+
+void gl_ctx_destroy(gl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->trees.clear();
+    c->fris.clear();
+    c->roots.clear();
+    c->lde_tables.clear();
+    c->in_stage.release(); c->vals.release(); c->scratch.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* gl_ctx_last_error(gl_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t gl_ctx_stream(gl_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+
+int gl_commit(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
+              int input_is_coeffs, uint64_t* out_coeffs, uint64_t* out_leaves, uint64_t* out_digests, uint64_t* out_cap,
+              gl_handle* out_batch) {
+    GL_API_BEGIN(c)
+    if (!cols) GL_THROW(GL_ERR_INVALID, "cols is NULL");
+    return commit_impl(c, cols, nullptr, 0, n_cols, log_n, rate_bits, cap_height, input_is_coeffs, out_coeffs, out_leaves,
+                       out_digests, out_cap, out_batch);
+    GL_API_END(c)
+}
+
+int gl_dev_commit(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                  uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_batch) {
+    GL_API_BEGIN(c)
+    if (!d_cols) GL_THROW(GL_ERR_INVALID, "d_cols is NULL");
+    return commit_impl(c, nullptr, d_cols, col_stride, n_cols, log_n, rate_bits, cap_height, input_is_coeffs, nullptr, nullptr,
+                       nullptr, out_cap, out_batch);
+    GL_API_END(c)
+}
+
+int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+               int input_is_coeffs, uint64_t* d_out_rows, uint32_t out_pitch, uint64_t* d_out_coeffs) {
+    GL_API_BEGIN(c)
+    check_shape(n_cols, log_n, rate_bits, 0);
+    if (!d_cols || !d_out_rows) GL_THROW(GL_ERR_INVALID, "NULL device pointer");
+    if (out_pitch % 8 || out_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "out_pitch must be a multiple of 8 and >= n_cols");
+    uint64_t* coeffs = d_out_coeffs;
+    if (!coeffs) { c->scratch.ensure(((uint64_t)1 << log_n) * out_pitch); coeffs = c->scratch.p; }
+    lde_stage(c, d_cols, col_stride, n_cols, log_n, rate_bits, input_is_coeffs, coeffs, out_pitch, d_out_rows, out_pitch, false);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_dev_repack(gl_ctx* c, const uint64_t* d_src, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst, uint32_t dst_pitch,
+                  uint32_t dst_col_off) {
+    GL_API_BEGIN(c)
+    if (!d_src || !d_dst || dst_col_off + src_cols > dst_pitch) GL_THROW(GL_ERR_INVALID, "bad repack arguments");
+    uint64_t total = n_rows * src_cols;
+    if (total) {
+        ntt::repitch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(d_src, src_cols, d_dst, dst_pitch, dst_col_off,
+                                                                                  src_cols, n_rows);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_dev_merkle(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch, uint32_t cap_height,
+                  uint64_t* d_digests, uint64_t* out_cap) {
+    GL_API_BEGIN(c)
+    if (!d_leaves || !out_cap) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) GL_THROW(GL_ERR_INVALID, "n_leaves must be a power of two");
+    if ((1ULL << cap_height) > n_leaves) GL_THROW(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len())");
+    if (pitch % 8 || pitch < leaf_len) GL_THROW(GL_ERR_INVALID, "pitch must be a multiple of 8 and >= leaf_len");
+    if (!d_digests && n_leaves > (1ULL << cap_height)) GL_THROW(GL_ERR_INVALID, "d_digests is NULL");
+    c->scratch.ensure(4ULL << cap_height);
+    merkle_build(c, d_leaves, n_leaves, leaf_len, pitch, cap_height, d_digests, c->scratch.p, nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(out_cap, c->scratch.p, 32ULL << cap_height, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_merkle_new(gl_ctx* c, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t cap_height,
+                  uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_tree) {
+    GL_API_BEGIN(c)
+    if (!leaves || !out_cap) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) GL_THROW(GL_ERR_INVALID, "n_leaves must be a power of two");
+    if (n_leaves > (1ULL << 31)) GL_THROW(GL_ERR_UNSUPPORTED, "too many leaves");
+    if ((1ULL << cap_height) > n_leaves)
+        GL_THROW(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len()) (cap_height=%u, leaves=%llu)", cap_height,
+                 (unsigned long long)n_leaves);
+    auto t = std::make_unique<Tree>();
+    const uint32_t pitch = round_up(leaf_len ? leaf_len : 1, 8);
+    const uint64_t n_dig = 2 * (n_leaves - (1ULL << cap_height));
+    t->n_leaves = n_leaves; t->leaf_len = leaf_len; t->pitch = pitch; t->cap_height = cap_height;
+    t->leaves.ensure(n_leaves * pitch);
+    t->digests.ensure(n_dig * 4);
+    t->d_cap.ensure(4ULL << cap_height);
+    t->cap.resize(4ULL << cap_height);
+    if (leaf_len)
+        CUDA_CHECK(cudaMemcpy2DAsync(t->leaves.p, (size_t)pitch * 8, leaves, (size_t)leaf_len * 8, (size_t)leaf_len * 8, n_leaves,
+                                     cudaMemcpyHostToDevice, c->stream));
+    merkle_build(c, t->leaves.p, n_leaves, leaf_len, pitch, cap_height, t->digests.p, t->d_cap.p, nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, 32ULL << cap_height, cudaMemcpyDeviceToHost, c->stream));
+    if (out_digests && n_dig)
+        CUDA_CHECK(cudaMemcpyAsync(out_digests, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(out_cap, t->cap.data(), 32ULL << cap_height);
+    if (out_tree) *out_tree = put_tree(c, std::move(t));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_info(gl_ctx* c, gl_handle h, gl_tree_info_t* out) {
+    GL_API_BEGIN(c)
+    if (!out) GL_THROW(GL_ERR_INVALID, "out is NULL");
+    Tree* t = find_tree(c, h);
+    out->n_leaves = t->n_leaves; out->leaf_len = t->leaf_len; out->cap_height = t->cap_height;
+    out->degree_log = t->degree_log; out->rate_bits = t->rate_bits; out->has_coeffs = t->has_coeffs; out->pitch = t->pitch;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_get(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_row) {
+    GL_API_BEGIN(c)
+    Tree* t = find_tree(c, h);
+    if (leaf_index >= t->n_leaves || !out_row) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
+    CUDA_CHECK(cudaMemcpyAsync(out_row, t->leaves.p + leaf_index * t->pitch, (size_t)t->leaf_len * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_get_lde_values(gl_ctx* c, gl_handle h, uint64_t index, uint64_t step, uint64_t* out_row) {
+    GL_API_BEGIN(c)
+    Tree* t = find_tree(c, h);
+    uint64_t i = index * step;
+    if (i >= t->n_leaves || !out_row) GL_THROW(GL_ERR_INVALID, "index * step out of range");
+    uint64_t row = h_bitrev((uint32_t)i, log2_exact(t->n_leaves));
+    CUDA_CHECK(cudaMemcpyAsync(out_row, t->leaves.p + row * t->pitch, (size_t)t->leaf_len * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_prove(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_siblings) {
+    GL_API_BEGIN(c)
+    Tree* t = find_tree(c, h);
+    if (leaf_index >= t->n_leaves || !out_siblings) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
+    uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
+    uint64_t L = 1ULL << log_sub, sub = leaf_index >> log_sub, j = leaf_index & (L - 1);
+    const uint64_t* base = t->digests.p + 4 * (sub * 2 * (L - 1));
+    for (uint32_t layer = 0; layer < log_sub; layer++) {
+        CUDA_CHECK(cudaMemcpyAsync(out_siblings + 4 * layer, base + 4 * merkle::digest_index(layer, j ^ 1), 32,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        j >>= 1;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_read(gl_ctx* c, gl_handle h, int part, uint64_t* out) {
+    GL_API_BEGIN(c)
+    Tree* t = find_tree(c, h);
+    if (!out) GL_THROW(GL_ERR_INVALID, "out is NULL");
+    switch (part) {
+        case GL_PART_COEFFS: {
+            if (!t->has_coeffs) GL_THROW(GL_ERR_INVALID, "tree has no coefficients");
+            uint64_t N = 1ULL << t->degree_log;
+            c->scratch.ensure(N * t->leaf_len);
+            dim3 tb(32, 8), tg((uint32_t)((N + 31) / 32), (t->leaf_len + 31) / 32);
+            ntt::transpose_out_kernel<<<tg, tb, 0, c->stream>>>(t->coeffs.p, t->pitch, c->scratch.p, N, t->leaf_len, N);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(out, c->scratch.p, N * t->leaf_len * 8, cudaMemcpyDeviceToHost, c->stream));
+            break;
+        }
+        case GL_PART_LEAVES:
+            if (t->leaf_len)
+                CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)t->leaf_len * 8, t->leaves.p, (size_t)t->pitch * 8, (size_t)t->leaf_len * 8,
+                                             t->n_leaves, cudaMemcpyDeviceToHost, c->stream));
+            break;
+        case GL_PART_DIGESTS: {
+            uint64_t n_dig = 2 * (t->n_leaves - (1ULL << t->cap_height));
+            if (n_dig) CUDA_CHECK(cudaMemcpyAsync(out, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));
+            break;
+        }
+        case GL_PART_CAP: memcpy(out, t->cap.data(), t->cap.size() * 8); break;
+        default: GL_THROW(GL_ERR_INVALID, "unknown part %d", part);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_tree_free(gl_ctx* c, gl_handle h) {
+    GL_API_BEGIN(c)
+    find_tree(c, h);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->trees.erase(h);
+    return GL_OK;
+    GL_API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------------ FRI
+int gl_fri_begin(gl_ctx* c, const uint64_t* coeffs_ext, const uint64_t* values_ext, uint64_t len, uint32_t rate_bits,
+                 uint32_t cap_height, gl_handle* out_fri) {
+    GL_API_BEGIN(c)
+    if (!coeffs_ext || !values_ext || !out_fri) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (len == 0 || (len & (len - 1)) || len > (1ULL << 31)) GL_THROW(GL_ERR_INVALID, "len must be a power of two");
+    auto f = std::make_unique<Fri>();
+    f->len = len; f->rate_bits = rate_bits; f->cap_height = cap_height;
+    f->coeffs.ensure(2 * len); f->values.ensure(2 * len); f->tmp.ensure(2 * len);
+    CUDA_CHECK(cudaMemcpyAsync(f->coeffs.p, coeffs_ext, 16 * len, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(f->tmp.p, values_ext, 16 * len, cudaMemcpyHostToDevice, c->stream));
+    fri::canon_kernel<<<(uint32_t)((2 * len + 255) / 256), 256, 0, c->stream>>>(f->coeffs.p, 2 * len);
+    CUDA_CHECK(cudaGetLastError());
+    uint32_t bits = log2_exact(len);
+    fri::bitrev_gather_ext_kernel<<<(uint32_t)((len + 255) / 256), 256, 0, c->stream>>>(
+        reinterpret_cast<const ulonglong2*>(f->tmp.p), reinterpret_cast<ulonglong2*>(f->values.p), bits);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    gl_handle h = c->next_handle++;
+    c->fris[h] = std::move(f);
+    *out_fri = h;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_fri_commit_layer(gl_ctx* c, gl_handle fh, uint32_t arity_bits, uint64_t* out_leaves, uint64_t* out_digests, uint64_t* out_cap,
+                        gl_handle* out_tree) {
+    GL_API_BEGIN(c)
+    Fri* f = find_fri(c, fh);
+    if (!out_cap) GL_THROW(GL_ERR_INVALID, "out_cap is NULL");
+    uint64_t arity = 1ULL << arity_bits;
+    if (arity > f->len) GL_THROW(GL_ERR_INVALID, "arity larger than the codeword");
+    uint64_t n_leaves = f->len >> arity_bits;
+    uint32_t leaf_len = (uint32_t)(2 * arity);
+    if ((1ULL << f->cap_height) > n_leaves) GL_THROW(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len())");
+    auto t = std::make_unique<Tree>();
+    const uint32_t pitch = round_up(leaf_len, 8);
+    const uint64_t n_dig = 2 * (n_leaves - (1ULL << f->cap_height));
+    t->n_leaves = n_leaves; t->leaf_len = leaf_len; t->pitch = pitch; t->cap_height = f->cap_height;
+    t->leaves.ensure(n_leaves * pitch);
+    t->digests.ensure(n_dig * 4);
+    t->d_cap.ensure(4ULL << f->cap_height);
+    t->cap.resize(4ULL << f->cap_height);
+    // bit-reversed values chunked by arity ARE the leaves (flatten = the [a0,a1] interleaving already in memory)
+    if (pitch == leaf_len) {
+        CUDA_CHECK(cudaMemcpyAsync(t->leaves.p, f->values.p, 16 * f->len, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        CUDA_CHECK(cudaMemcpy2DAsync(t->leaves.p, (size_t)pitch * 8, f->values.p, (size_t)leaf_len * 8, (size_t)leaf_len * 8, n_leaves,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+    }
+    merkle_build(c, t->leaves.p, n_leaves, leaf_len, pitch, f->cap_height, t->digests.p, t->d_cap.p, nullptr, nullptr, nullptr);
+    CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, 32ULL << f->cap_height, cudaMemcpyDeviceToHost, c->stream));
+    if (out_leaves)
+        CUDA_CHECK(cudaMemcpy2DAsync(out_leaves, (size_t)leaf_len * 8, t->leaves.p, (size_t)pitch * 8, (size_t)leaf_len * 8, n_leaves,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    if (out_digests && n_dig)
+        CUDA_CHECK(cudaMemcpyAsync(out_digests, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(out_cap, t->cap.data(), 32ULL << f->cap_height);
+    if (out_tree) *out_tree = put_tree(c, std::move(t));
+    f->last_arity_bits = arity_bits;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_fri_fold(gl_ctx* c, gl_handle fh, const uint64_t beta[2]) {
+    GL_API_BEGIN(c)
+    Fri* f = find_fri(c, fh);
+    if (!beta) GL_THROW(GL_ERR_INVALID, "beta is NULL");
+    if (f->last_arity_bits == 0) GL_THROW(GL_ERR_INVALID, "gl_fri_fold without a preceding gl_fri_commit_layer");
+    const uint32_t arity_bits = f->last_arity_bits;   // upstream folds by the arity of the layer it just committed
+    f->last_arity_bits = 0;
+    uint64_t arity = 1ULL << arity_bits;
+    if (arity > f->len) GL_THROW(GL_ERR_INVALID, "arity larger than the codeword");
+    uint64_t n_out = f->len >> arity_bits;
+    fri::fold_kernel<<<(uint32_t)((n_out + 127) / 128), 128, 0, c->stream>>>(
+        reinterpret_cast<const ulonglong2*>(f->coeffs.p), reinterpret_cast<ulonglong2*>(f->tmp.p), (uint32_t)n_out, (uint32_t)arity,
+        gl::canon(beta[0]), gl::canon(beta[1]));
+    CUDA_CHECK(cudaGetLastError());
+    std::swap(f->coeffs.p, f->tmp.p);
+    std::swap(f->coeffs.words, f->tmp.words);
+    f->len = n_out;
+    f->shift = gl::h_pow(f->shift, arity);
+    // values <- coset_fft(coeffs, shift), kept in bit-reversed (in-place DIF) order
+    uint32_t log_len = log2_exact(n_out);
+    CosetTable tab;
+    fill_coset_table(c, tab, f->shift, log_len);
+    run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, &tab, 2, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_fri_final_poly(gl_ctx* c, gl_handle fh, uint64_t* out, uint64_t* out_len) {
+    GL_API_BEGIN(c)
+    Fri* f = find_fri(c, fh);
+    uint64_t n = f->len >> f->rate_bits;
+    if (out_len) *out_len = n;
+    if (out && n) CUDA_CHECK(cudaMemcpyAsync(out, f->coeffs.p, 16 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_fri_end(gl_ctx* c, gl_handle fh) {
+    GL_API_BEGIN(c)
+    find_fri(c, fh);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->fris.erase(fh);
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_poseidon_permute(gl_ctx* c, uint64_t* states, uint64_t n) {
+    GL_API_BEGIN(c)
+    if (!states && n) GL_THROW(GL_ERR_INVALID, "states is NULL");
+    if (n == 0) return GL_OK;
+    c->scratch.ensure(12 * n);
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p, states, 96 * n, cudaMemcpyHostToDevice, c->stream));
+    merkle::permute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, c->stream>>>(c->scratch.p, n);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(states, c->scratch.p, 96 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_ctx_stage_times(gl_ctx* c, float* out_ms, uint32_t* out_launches) {
+    if (!c || !out_ms) return GL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    memcpy(out_ms, c->stage_ms, sizeof c->stage_ms);
+    if (out_launches) memcpy(out_launches, c->launches, sizeof c->launches);
+    return GL_OK;
+}
+
+int gl_microbench(gl_ctx* c, int which, uint32_t iters, double* out_ops_per_s) {
+    GL_API_BEGIN(c)
+    if (!out_ops_per_s || iters == 0) GL_THROW(GL_ERR_INVALID, "bad arguments");
+    const int threads = 256;
+    const int blocks = c->sm_count * (which == 4 ? 4 : 8);
+    c->scratch.ensure((size_t)threads * blocks);
+    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
+    double ops = 0;
+    for (int rep = 0; rep < 2; rep++) {   // first repetition warms up
+        CUDA_CHECK(cudaEventRecord(e0, c->stream));
+        switch (which) {
+            case 0: microbench::imad_wide_kernel<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters, 0x9E3779B9u); break;
+            case 1: microbench::alu_kernel<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters, 0x9E3779B9u); break;
+            case 2: microbench::mixed_kernel<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters, 0x9E3779B9u); break;
+            case 3: microbench::modmul_kernel<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters, 0x123456789ABCDEF1ULL); break;
+            case 4: microbench::poseidon_kernel<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters); break;
+            default: GL_THROW(GL_ERR_INVALID, "unknown microbenchmark %d", which);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaEventRecord(e1, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        double per_thread = which == 4 ? (double)iters : (which == 2 ? 2.0 : 1.0) * 4.0 * microbench::CHAINS * iters;
+        ops = per_thread * threads * blocks / (ms * 1e-3);
+    }
+    *out_ops_per_s = ops;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+void* gl_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void gl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

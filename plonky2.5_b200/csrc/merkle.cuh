@@ -1,0 +1,95 @@
+// K4/K5: Poseidon Merkle tree in plonky2's interleaved digest layout.
+//
+// Replaces plonky2 hash/src/merkle_tree.rs · MerkleTree::new / fill_digests_buf / fill_subtree and
+// plonk/config.rs · Hasher::hash_or_noop, hash/hashing.rs · compress (semantics SURVEY.md A.5, A.6).
+// Driven in the reference from /root/reference/src/p3/mod.rs:250 and :260 (every PolynomialBatch commit and every
+// FRI commit-phase layer builds one tree).
+//
+// Layout: leaves are a row-major device matrix [n_leaves][pitch] (pitch multiple of 8 words = 64 B);
+// digests = 2*(n_leaves - 2^cap_height) HashOuts; subtree t occupies [t*2(L-1), (t+1)*2(L-1)); inside a subtree the
+// node j of layer i (0 = leaf digests) sits at 2*(((j>>1) << (i+1)) + (1<<i) - 1) + (j&1); roots go to cap[t].
+#pragma once
+#include "poseidon.cuh"
+
+namespace merkle {
+
+__host__ __device__ __forceinline__ uint64_t digest_index(uint32_t layer, uint64_t j) {
+    return 2 * (((j >> 1) << (layer + 1)) + (1ULL << layer) - 1) + (j & 1);
+}
+
+__device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[poseidon::WIDTH]) {
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(dst);
+    d[0] = make_ulonglong2(gl::canon(s[0]), gl::canon(s[1]));
+    d[1] = make_ulonglong2(gl::canon(s[2]), gl::canon(s[3]));
+}
+
+// One thread per leaf: hash_or_noop(row) with the overwrite-mode rate-8 sponge.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+leaf_hash_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t leaf_len, uint64_t n_leaves,
+                 uint32_t log_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
+    uint64_t leaf = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    const uint64_t* row = leaves + leaf * pitch;
+    uint64_t s[poseidon::WIDTH];
+#pragma unroll
+    for (int i = 0; i < poseidon::WIDTH; i++) s[i] = 0;
+    if (leaf_len <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if ((uint32_t)i < leaf_len) s[i] = row[i];   // hash_or_noop: no permutation
+    } else {
+        const uint32_t n_chunks = (leaf_len + 7) >> 3;
+#pragma unroll 1
+        for (uint32_t k = 0; k < n_chunks; k++) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(row + 8 * k);
+            ulonglong2 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+            uint64_t in[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
+            const uint32_t rem = leaf_len - 8 * k;   // >= 1
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if ((uint32_t)i < rem) s[i] = in[i];   // overwrite mode: a short last chunk keeps the other lanes
+            poseidon::permute(s);
+        }
+    }
+    uint64_t* dst;
+    if (log_sub == 0) dst = cap + 4 * leaf;
+    else {
+        uint64_t L = 1ULL << log_sub, t = leaf >> log_sub, j = leaf & (L - 1);
+        dst = digests + 4 * (t * 2 * (L - 1) + digest_index(0, j));
+    }
+    store_digest(dst, s);
+}
+
+// One thread per node of layer `layer` (1..log_sub): two_to_one(children).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+tree_level_kernel(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, uint32_t layer, uint32_t log_sub,
+                  uint64_t n_nodes) {
+    uint64_t node = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (node >= n_nodes) return;
+    const uint32_t lw = log_sub - layer;                 // log2(nodes of this layer per subtree)
+    const uint64_t t = node >> lw, j = node & ((1ULL << lw) - 1);
+    const uint64_t L = 1ULL << log_sub;
+    uint64_t* base = digests + 4 * (t * 2 * (L - 1));
+    const ulonglong2* ch = reinterpret_cast<const ulonglong2*>(base + 4 * digest_index(layer - 1, 2 * j));
+    ulonglong2 a = ch[0], b = ch[1], c = ch[2], d = ch[3];   // left digest then right digest (adjacent)
+    uint64_t s[poseidon::WIDTH] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
+    poseidon::permute(s);
+    uint64_t* dst = (layer == log_sub) ? cap + 4 * t : base + 4 * digest_index(layer, j);
+    store_digest(dst, s);
+}
+
+// Batch of independent permutations (host challenger / PoW plumbing): states[n][12] in place, canonical out.
+__global__ void permute_kernel(uint64_t* __restrict__ states, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s[poseidon::WIDTH];
+#pragma unroll
+    for (int k = 0; k < poseidon::WIDTH; k++) s[k] = states[12 * i + k];
+    poseidon::permute(s);
+#pragma unroll
+    for (int k = 0; k < poseidon::WIDTH; k++) states[12 * i + k] = gl::canon(s[k]);
+}
+
+}  // namespace merkle

@@ -1,0 +1,218 @@
+// K1/K2/K3: batched Goldilocks NTT over a ROW-MAJOR matrix [rows][pitch] (one column = one polynomial).
+//
+// Replaces plonky2 field/src/fft.rs · fft_classic / ifft_with_options, field/src/polynomial/mod.rs · lde /
+// coset_fft_with_options, and util/src/lib.rs · transpose + reverse_index_bits_in_place;
+// driven from /root/reference/src/p3/mod.rs:250,260 through PolynomialBatch::from_values / from_coeffs.
+//
+// Why row-major: the Merkle leaves are rows, so the LDE must END row-major with bit-reversed row order.  Keeping
+// the matrix row-major through every pass means (i) every HBM access is a G-column segment of a row (32/64 B,
+// sector aligned because pitch % 8 == 0) whatever row permutation a pass needs, (ii) an in-place decimation-in-
+// frequency NTT leaves row p holding X[bitrev(p)] — exactly plonky2's leaf order — so the "transpose +
+// reverse_index_bits" stage of the reference costs nothing here, and (iii) the iFFT's index reversal
+// out[i] = b[(n-i) mod n] is just the store address of the last pass.
+//
+// One pass = a 2^a-point DIF NTT (a <= 10) on index bits [log_blk-a, log_blk) of every block of 2^log_blk rows,
+// staged through shared memory in radix-8 register rounds, followed (if lower bits remain) by the inter-pass
+// twiddle w_{2^log_blk}^(o_lo * bitrev_a(l)) (four-step factorisation).  Stage twiddles come from a 2^(a-1)-entry
+// shared-memory table; all roots come from one table W[e] = w_N^e (e < N/2) held by the context.
+#pragma once
+#include "gl_field.cuh"
+
+namespace ntt {
+
+struct PassParams {
+    const uint64_t* src;
+    uint64_t* dst;
+    uint32_t src_pitch, dst_pitch;   // words
+    uint32_t log_n;                  // NTT size
+    uint32_t log_blk;                // block size entering this pass (log_n for the first pass)
+    uint32_t a;                      // stages done in this pass (>= 3)
+    uint32_t ncg;                    // column groups (pitch / G)
+    const uint64_t* W;               // w_N^e, e < max(N/2, 1), canonical
+    const uint64_t* preA;            // coset pre-scale (first pass only) g^(l << (log_n-a)), l < 2^a, or nullptr
+    const uint64_t* preB;            //                                   g^(o_lo), o_lo < 2^(log_n-a)
+    uint32_t store_mode;             // 0: row p -> p ; 1: iFFT: row p -> (N - bitrev_n(p)) mod N
+    uint64_t scale;                  // multiply at store when != 1 (1/N for the iFFT)
+};
+
+__device__ __forceinline__ uint32_t ins3(uint32_t q, uint32_t sh, uint32_t e) {
+    return ((q >> sh) << (sh + 3)) | (e << sh) | (q & ((1u << sh) - 1));
+}
+__device__ __forceinline__ uint32_t phys_row(uint32_t l) { return l + (l >> 3); }   // bank-conflict padding
+
+__device__ __forceinline__ void bfly(uint64_t& u, uint64_t& v, uint64_t tw) {
+    uint64_t s = gl::add(u, v);
+    uint64_t d = gl::sub(u, v);
+    u = s;
+    v = gl::mulc(d, tw);
+}
+
+// stages on thread-local bits k = nst-1 .. 0 of the 8 register elements; tile bit of local bit k is sh + k
+__device__ __forceinline__ void radix8_round(uint64_t (&x)[8], const uint64_t* __restrict__ Wl, uint32_t a,
+                                             uint32_t sh, uint32_t qlo, uint32_t nst) {
+    if (nst >= 3) {
+        const uint32_t shift = a - (sh + 2) - 1;
+#pragma unroll
+        for (int e = 0; e < 4; e++) bfly(x[e], x[e + 4], Wl[(((uint32_t)e << sh) | qlo) << shift]);
+    }
+    if (nst >= 2) {
+        const uint32_t shift = a - (sh + 1) - 1;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            uint64_t tw = Wl[(((uint32_t)e << sh) | qlo) << shift];
+            bfly(x[e], x[e + 2], tw);
+            bfly(x[e + 4], x[e + 6], tw);
+        }
+    }
+    {
+        const uint32_t shift = a - sh - 1;
+        uint64_t tw = Wl[qlo << shift];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) bfly(x[e], x[e + 1], tw);
+    }
+}
+
+template <int G>
+__global__ void ntt_pass_kernel(const PassParams p) {
+    extern __shared__ uint64_t sm[];
+    const uint32_t a = p.a, T = 1u << a;
+    uint64_t* tile = sm;
+    uint64_t* Wl = sm + (size_t)(T + (T >> 3)) * G;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;   // nthr = T*G/8
+    const uint32_t c = tid % G, q = tid / G;
+    const uint32_t cg = blockIdx.x % p.ncg, tile_id = blockIdx.x / p.ncg;
+    const uint32_t b_lo = p.log_blk - a;
+    const uint32_t o_lo = tile_id & ((1u << b_lo) - 1), o_hi = tile_id >> b_lo;
+    const uint32_t row_base = (o_hi << p.log_blk) | o_lo;
+    const uint32_t col = cg * G + c;
+
+    for (uint32_t e = tid; e < (T >> 1); e += nthr) Wl[e] = p.W[(size_t)e << (p.log_n - a)];
+
+    uint64_t x[8];
+    uint32_t sh = a - 3;
+    {
+        uint64_t bv = 1;
+        const bool pre = p.preA != nullptr;
+        if (pre && b_lo) bv = p.preB[o_lo];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            uint32_t l = ins3(q, sh, e);
+            uint64_t row = row_base | ((uint64_t)l << b_lo);
+            uint64_t v = p.src[row * p.src_pitch + col];
+            if (pre) {
+                uint64_t f = p.preA[l];
+                if (b_lo) f = gl::mul(f, bv);
+                v = gl::mulc(v, f);
+            }
+            x[e] = v;
+        }
+    }
+    __syncthreads();   // Wl ready
+    uint32_t remaining = a;
+    while (true) {
+        const uint32_t nst = remaining >= 3 ? 3 : remaining;
+        radix8_round(x, Wl, a, sh, q & ((1u << sh) - 1), nst);
+        remaining -= nst;
+        if (remaining == 0) break;
+#pragma unroll
+        for (int e = 0; e < 8; e++) tile[(size_t)phys_row(ins3(q, sh, e)) * G + c] = x[e];
+        __syncthreads();
+        sh = remaining >= 3 ? remaining - 3 : 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = tile[(size_t)phys_row(ins3(q, sh, e)) * G + c];
+        __syncthreads();
+    }
+    // sh is the shift of the last round: element e of this thread is tile row l = ins3(q, sh, e)
+    const uint32_t N = 1u << p.log_n;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        uint32_t l = ins3(q, sh, e);
+        uint64_t v = x[e];
+        if (b_lo) {
+            // inter-pass twiddle w_{2^log_blk}^(o_lo * bitrev_a(l)), looked up in W (w_N^e, e < N/2)
+            uint32_t ex = (o_lo * gl::bitrev32(l, a)) << (p.log_n - p.log_blk);
+            uint64_t w;
+            if (ex >= (N >> 1)) w = gl::P - p.W[ex - (N >> 1)];
+            else w = p.W[ex];
+            v = gl::mulc(v, w);
+        }
+        if (p.scale != 1) v = gl::mulc(v, p.scale);
+        uint32_t prow = row_base | (l << b_lo);
+        uint32_t drow = p.store_mode == 1 ? ((N - gl::bitrev32(prow, p.log_n)) & (N - 1)) : prow;
+        p.dst[(uint64_t)drow * p.dst_pitch + col] = v;
+    }
+}
+
+// NTT sizes 1, 2, 4 (log_n < 3): direct O(N^2) evaluation, one thread per (output row, column).
+// Produces the same in-place-DIF order (row p holds X[bitrev(p)]) / iFFT order as the pass kernel.
+__global__ void ntt_tiny_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint32_t src_pitch,
+                                uint32_t dst_pitch, uint32_t n_cols, uint32_t log_n, uint64_t root, uint64_t g,
+                                uint32_t store_mode, uint64_t scale) {
+    const uint32_t N = 1u << log_n;
+    uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t p = blockIdx.y;
+    if (col >= n_cols) return;
+    uint32_t k = gl::bitrev32(p, log_n);
+    // X[k] = sum_j x_j g^j root^(jk)
+    uint64_t wk = 1;
+    for (uint32_t i = 0; i < k; i++) wk = gl::mulc(wk, root);
+    uint64_t step = gl::mulc(wk, g), cur = 1, acc = 0;
+    for (uint32_t j = 0; j < N; j++) {
+        acc = gl::add(acc, gl::mulc(src[(uint64_t)j * src_pitch + col], cur));
+        cur = gl::mulc(cur, step);
+    }
+    if (scale != 1) acc = gl::mulc(acc, scale);
+    uint32_t drow = store_mode == 1 ? ((N - k) & (N - 1)) : p;
+    dst[(uint64_t)drow * dst_pitch + col] = acc;
+}
+
+// Column-major [n_cols][n_rows] (contiguous columns, as plonky2's Vec<PolynomialValues>) -> row-major
+// [n_rows][pitch], canonicalising on the way.  32x32 tiles through shared memory.
+__global__ void transpose_in_kernel(const uint64_t* __restrict__ src, uint64_t src_col_stride, uint64_t* __restrict__ dst,
+                                    uint32_t pitch, uint32_t n_cols, uint64_t n_rows) {
+    __shared__ uint64_t t[32][33];
+    uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    uint32_t c0 = blockIdx.y * 32;
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint32_t c = c0 + i;
+        uint64_t r = r0 + threadIdx.x;
+        t[i][threadIdx.x] = (c < n_cols && r < n_rows) ? gl::canon(src[c * src_col_stride + r]) : 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint64_t r = r0 + i;
+        uint32_t c = c0 + threadIdx.x;
+        if (r < n_rows && c < pitch) dst[r * pitch + c] = t[threadIdx.x][i];
+    }
+}
+
+// Row-major [n_rows][pitch] -> column-major [n_cols][n_rows]
+__global__ void transpose_out_kernel(const uint64_t* __restrict__ src, uint32_t pitch, uint64_t* __restrict__ dst,
+                                     uint64_t dst_col_stride, uint32_t n_cols, uint64_t n_rows) {
+    __shared__ uint64_t t[32][33];
+    uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    uint32_t c0 = blockIdx.y * 32;
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint64_t r = r0 + i;
+        uint32_t c = c0 + threadIdx.x;
+        t[i][threadIdx.x] = (r < n_rows && c < n_cols) ? src[r * pitch + c] : 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint32_t c = c0 + i;
+        uint64_t r = r0 + threadIdx.x;
+        if (c < n_cols && r < n_rows) dst[c * dst_col_stride + r] = t[threadIdx.x][i];
+    }
+}
+
+// Row-major [n_rows][src_pitch] -> row-major [n_rows][dst_pitch] (n_cols copied, canonicalised, padding zeroed);
+// used when MerkleTree::new leaves arrive packed from the host and for multi-GPU repacking.
+__global__ void repitch_kernel(const uint64_t* __restrict__ src, uint64_t src_pitch, uint64_t* __restrict__ dst,
+                               uint32_t dst_pitch, uint32_t dst_col_off, uint32_t n_cols, uint64_t n_rows) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t r = i / n_cols;
+    uint32_t c = (uint32_t)(i % n_cols);
+    if (r < n_rows) dst[r * dst_pitch + dst_col_off + c] = gl::canon(src[r * src_pitch + c]);
+}
+
+}  // namespace ntt

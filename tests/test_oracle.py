@@ -1,0 +1,225 @@
+"""CPU tests of the oracle itself: golden vectors the reference holds, Python-vs-C cross-restatement, and the
+oracle-independent algebraic invariants of SURVEY.md A.9.  No GPU needed."""
+import hashlib
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import gl_oracle as o
+from oracle_c import P, splitmix_columns
+
+
+def test_round_constants_pinned():
+    rc = o.ALL_ROUND_CONSTANTS
+    assert len(rc) == 360 and all(c < o.P for c in rc)
+    assert rc[0] == 0xB585F766F2144405 and rc[359] == 0xBC8DFB627FE558FC
+    assert hashlib.sha256(b"".join(struct.pack("<Q", c) for c in rc)).hexdigest() == o.ROUND_CONSTANTS_SHA256
+
+
+def test_generated_headers_match_constants():
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel in ("oracle/poseidon_constants.h", "plonky2.5_b200/csrc/poseidon_constants.cuh"):
+        vals = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", open(os.path.join(root, rel)).read())]
+        assert vals == o.ALL_ROUND_CONSTANTS, rel
+
+
+def test_poseidon_kat_reference_vectors(golden, oc):
+    """/root/reference/src/common/poseidon2/poseidon2_goldilocks.rs:190-211"""
+    for v in golden["poseidon_kat"]["vectors"]:
+        assert o.poseidon(v["input"]) == v["output"]
+        assert oc.poseidon(v["input"]).tolist() == v["output"]
+
+
+def test_field_constants(golden, oc):
+    fc = golden["field_constants"]
+    assert fc["modulus"] == o.P == P
+    g2 = fc["power_of_two_generator"]
+    assert pow(7, (o.P - 1) >> 32, o.P) == g2
+    assert pow(g2, 1 << 31, o.P) == o.P - 1 and pow(g2, 1 << 32, o.P) == 1
+    assert oc.lib.glo_root_of_unity(3) == o.primitive_root_of_unity(3) == pow(2, 24 * 5, o.P)  # w_8 = 2^120
+
+
+def test_derived_anchors(golden, oc):
+    a = golden["derived_anchors"]
+    h = o.hash_no_pad(list(range(135)))
+    assert h == a["hash_no_pad_0_134"]
+    assert oc.hash_or_noop(np.arange(135, dtype=np.uint64)).tolist() == h
+    assert o.two_to_one(h, h) == a["two_to_one_h_h"] == oc.two_to_one(h, h).tolist()
+    t = a["tiny_commit"]
+    pb = o.PolynomialBatch.from_values(t["values"], t["rate_bits"], t["cap_height"])
+    assert pb.polynomials == t["coeffs"] and pb.merkle_tree.leaves == t["leaves"]
+    # naive O(n^2) evaluation agrees with the radix-2 recursion
+    for col, cf in zip(t["values"], t["coeffs"]):
+        assert o.fft_naive(cf) == [v % o.P for v in col]
+
+
+def test_hash_or_noop_modes(oc):
+    rng = random.Random(5)
+    for n in (0, 1, 3, 4):
+        row = [rng.randrange(o.P) for _ in range(n)]
+        assert o.hash_or_noop(row) == row + [0] * (4 - n)
+        assert oc.hash_or_noop(np.array(row, dtype=np.uint64)).tolist() == row + [0] * (4 - n)
+    for n in (5, 7, 8, 9, 16, 17, 135):
+        row = [rng.randrange(o.P) for _ in range(n)]
+        assert oc.hash_or_noop(np.array(row, dtype=np.uint64)).tolist() == o.hash_no_pad(row)
+    # overwrite mode: a short last chunk keeps lanes of the previous state => differs from zero-padding
+    row = [rng.randrange(o.P) for _ in range(9)]
+    assert o.hash_no_pad(row) != o.hash_no_pad(row + [0] * 7)
+
+
+def test_non_canonical_inputs_are_reduced(oc):
+    row = np.array([o.P, o.P + 5, 2**64 - 1, 0, 1, 2, 3, 4, 5], dtype=np.uint64)
+    assert oc.hash_or_noop(row).tolist() == o.hash_no_pad([int(x) % o.P for x in row])
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8])
+def test_fft_ifft_c_vs_python(oc, log_n):
+    rng = random.Random(log_n)
+    v = [rng.randrange(o.P) for _ in range(1 << log_n)]
+    assert oc.fft(v).tolist() == o.fft(v)
+    assert oc.ifft(v).tolist() == o.ifft(v)
+    assert oc.fft(oc.ifft(v)).tolist() == v
+    assert oc.coset_fft(v, 7).tolist() == o.coset_fft(v, 7)
+    if log_n <= 5:
+        assert o.fft_naive(v) == o.fft(v)
+
+
+@pytest.mark.parametrize("shape", [(0, 6, 2, 1), (1, 4, 1, 1), (2, 2, 1, 0), (3, 5, 2, 1), (4, 9, 3, 4), (5, 3, 1, 2),
+                                   (3, 135, 3, 2), (3, 2, 3, 6), (4, 4, 0, 0)])
+def test_commit_c_vs_python(oc, shape):
+    log_n, n_cols, r, h = shape
+    cols = splitmix_columns(100 + log_n, n_cols, 1 << log_n)
+    pb = o.PolynomialBatch.from_values([c.tolist() for c in cols], r, h)
+    res = oc.commit(cols, r, h)
+    assert res["coeffs"].tolist() == pb.polynomials
+    assert res["leaves"].tolist() == pb.merkle_tree.leaves
+    assert res["digests"].tolist() == pb.merkle_tree.digests
+    assert res["cap"].tolist() == pb.merkle_tree.cap
+    res2 = oc.commit(res["coeffs"], r, h, is_coeffs=True)
+    assert np.array_equal(res2["leaves"], res["leaves"]) and np.array_equal(res2["cap"], res["cap"])
+
+
+def test_commit_golden_fixture(oc, golden):
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u8").tobytes()).hexdigest()
+    for c in golden["commit_small"]["cases"]:
+        cols = splitmix_columns(c["seed"], c["n_cols"], 1 << c["log_n"])
+        res = oc.commit(cols, c["rate_bits"], c["cap_height"], bool(c["is_coeffs"]))
+        assert res["cap"].reshape(-1).tolist() == c["cap"]
+        assert sha(res["coeffs"]) == c["sha256_coeffs"] and sha(res["leaves"]) == c["sha256_leaves"]
+        assert sha(res["digests"]) == c["sha256_digests"]
+
+
+def test_invariant_leaves_are_horner_evaluations(oc):
+    """A.9(i): leaves[i][j] == P_j(7 * w_R^bitrev(i)) — independent of any FFT code."""
+    log_n, n_cols, r = 6, 5, 3
+    cols = splitmix_columns(7, n_cols, 1 << log_n)
+    res = oc.commit(cols, r, 2)
+    bits = log_n + r
+    w = o.primitive_root_of_unity(bits)
+    rng = random.Random(1)
+    for i in [0, 1, (1 << bits) - 1] + [rng.randrange(1 << bits) for _ in range(20)]:
+        x = 7 * pow(w, o.reverse_bits(i, bits), o.P) % o.P
+        for j in range(n_cols):
+            assert int(res["leaves"][i][j]) == o.eval_poly(res["coeffs"][j].tolist(), x)
+    # and the coefficients interpolate the input values on the subgroup
+    wn = o.primitive_root_of_unity(log_n)
+    for k in (0, 1, 17, 63):
+        for j in range(n_cols):
+            assert o.eval_poly(res["coeffs"][j].tolist(), pow(wn, k, o.P)) == int(cols[j][k])
+
+
+def test_invariant_merkle_paths_verify_with_verifier_rule(oc):
+    """A.9(iii): closed-form prove indices + verifier rule, for the C layout, incl. cap_height == log2(n)."""
+    for (log_l, ll, h) in [(3, 7, 0), (4, 135, 2), (6, 32, 4), (4, 5, 4), (7, 9, 3), (5, 3, 1)]:
+        leaves = splitmix_columns(log_l * 31 + ll, 1 << log_l, ll)
+        dig, cap = oc.merkle_new(leaves, h)
+        tree = o.MerkleTree([r.tolist() for r in leaves], h) if ll <= 9 or log_l <= 4 else None
+        if tree is not None:
+            assert dig.tolist() == tree.digests and cap.tolist() == tree.cap
+        sub = (1 << log_l) >> h
+        per = 2 * (sub - 1)
+        for idx in range(1 << log_l):
+            t, j = divmod(idx, sub)
+            sibs = []
+            for layer in range(sub.bit_length() - 1):
+                sibs.append(dig[t * per + o.digest_index(layer, j ^ 1)])
+                j >>= 1
+            assert oc.verify_path(leaves[idx], idx, sibs, cap)
+        if sub > 1:
+            bad = leaves[0].copy()
+            bad[0] ^= np.uint64(1)
+            t, j = 0, 0
+            sibs = [dig[o.digest_index(layer, (0 >> layer) ^ 1)] for layer in range(sub.bit_length() - 1)]
+            assert not oc.verify_path(bad, 0, sibs, cap)
+
+
+def test_merkle_rejects_oversized_cap(oc):
+    with pytest.raises(ValueError):
+        oc.merkle_new(np.zeros((4, 5), dtype=np.uint64), 3)
+    with pytest.raises(AssertionError):
+        o.MerkleTree([[1, 2, 3, 4, 5]] * 4, 3)
+
+
+def test_challenger_c_vs_python(oc):
+    rng = random.Random(3)
+    cp, cc = o.Challenger(), oc.new_challenger()
+    for step in range(40):
+        k = rng.randrange(1, 13)
+        es = [rng.randrange(o.P) for _ in range(k)]
+        cp.observe_elements(es)
+        cc.observe_elements(es)
+        for _ in range(rng.randrange(0, 4)):
+            assert cp.get_challenge() == cc.get_challenge()
+
+
+def _fri_inputs(log_len, rate_bits, seed):
+    """coeffs with the upper (1 - 2^-r) fraction zero, values = coset_fft(coeffs, 7)."""
+    n = 1 << log_len
+    low = n >> rate_bits
+    rng = random.Random(seed)
+    coeffs = [(rng.randrange(o.P), rng.randrange(o.P)) if i < low else (0, 0) for i in range(n)]
+    values = o.ext_coset_fft(coeffs, 7)
+    return coeffs, values
+
+
+@pytest.mark.parametrize("cfg", [(8, 3, 1, [4]), (9, 1, 2, [2, 3]), (10, 3, 2, [4, 4])])
+def test_fri_committed_trees_c_vs_python_and_fold_invariant(oc, cfg):
+    log_len, rate_bits, cap_h, arities = cfg
+    coeffs, values = _fri_inputs(log_len, rate_bits, log_len)
+    cp, cc = o.Challenger(), oc.new_challenger()
+    seed_obs = [11, 22, 33]
+    cp.observe_elements(seed_obs); cc.observe_elements(seed_obs)
+    trees, final = o.fri_committed_trees(coeffs, values, cp, arities, rate_bits, cap_h)
+    res = oc.fri_committed_trees(np.array(coeffs, dtype=np.uint64), np.array(values, dtype=np.uint64), arities, rate_bits, cap_h, cc)
+    for t, lv, dg, cap in zip(trees, res["leaves"], res["digests"], res["caps"]):
+        assert lv.tolist() == t.leaves and cap.tolist() == t.cap
+        if t.digests:
+            assert dg.tolist() == t.digests
+    assert res["final_poly"].tolist() == [list(c) for c in final]
+    assert cp.get_challenge() == cc.get_challenge()          # transcripts stayed in lock-step
+    # A.9(iv): the folded codeword evaluates the beta-combination of the decimated polynomials: check layer 1 by Horner
+    beta = tuple(int(x) for x in res["betas"][0])
+    arity = 1 << arities[0]
+    folded = []
+    for m in range(len(coeffs) // arity):
+        acc = (0, 0)
+        for c in reversed(coeffs[arity * m:arity * m + arity]):
+            acc = o.ext_add(o.ext_mul(acc, beta), c)
+        folded.append(acc)
+    if len(arities) > 1:
+        shift = pow(7, arity, o.P)
+        bits = log_len - arities[0]
+        w = o.primitive_root_of_unity(bits)
+        lv1 = res["leaves"][1].reshape(-1, 2)
+        for i in (0, 1, 5, (1 << bits) - 1):
+            x = shift * pow(w, o.reverse_bits(i, bits), o.P) % o.P
+            assert tuple(int(v) for v in lv1[i]) == o.ext_eval_poly(folded, x)
+
+
+def test_reduction_arity_bits_standard_recursion():
+    # ConstantArityBits(4, 5), rate_bits 3, cap_height 4 (standard_recursion_config, src/p3/mod.rs:231)
+    assert o.reduction_arity_bits_constant(4, 5, 16, 3, 4) == [4, 4, 4]
+    assert o.reduction_arity_bits_constant(4, 5, 13, 3, 4) == [4, 4]
