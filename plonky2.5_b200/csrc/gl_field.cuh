@@ -19,19 +19,56 @@ constexpr uint64_t EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 
 __host__ __device__ __forceinline__ uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
 
-// 128 -> 64 ("any"): lo + 2^64*hi, with 2^64 = 2^32 - 1 and 2^96 = -1 (mod p)
+// (z3:z2:z1:z0) -> 64 bits ("any"):  2^64 = 2^32 - 1 and 2^96 = -1 (mod p), so the value is X - z3 + z2*(2^32 - 1) with
+// X = (z1:z0).  The three 64-bit wrap-arounds (one borrow each from "- z3" and "- z2", one carry from "+ z2*2^32") are
+// collected in d in {-1, 0, 1} and folded back once as d*(2^32 - 1); a second wrap is impossible (tools/word_model.py
+// checks this instruction sequence against big-integer arithmetic).  Written in PTX because the data flow through the
+// carry flag is what keeps this at 12 integer instructions; nvcc's C++ lowering needs ~17 (64-bit compares + selects).
+__device__ __forceinline__ uint64_t reduce_words(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3) {
+    uint32_t l, h;
+    asm("{\n\t.reg .u32 d, ds;\n\t"
+        "sub.cc.u32  %0, %2, %5;\n\t"
+        "subc.cc.u32 %1, %3, 0;\n\t"
+        "subc.u32    d, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, %4;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32    d, d, 0;\n\t"
+        "add.cc.u32  %1, %1, %4;\n\t"
+        "addc.u32    d, d, 0;\n\t"
+        "shr.s32     ds, d, 31;\n\t"
+        "sub.cc.u32  %0, %0, d;\n\t"
+        "subc.u32    %1, %1, ds;\n\t"
+        "add.u32     %1, %1, d;\n\t"
+        "}" : "=&r"(l), "=&r"(h) : "r"(z0), "r"(z1), "r"(z2), "r"(z3));
+    return ((uint64_t)h << 32) | l;
+}
 __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
-    uint32_t hl = (uint32_t)hi;
-    uint64_t hh = hi >> 32;
-    uint64_t t0 = lo - hh;
-    if (lo < hh) t0 -= EPS;                 // borrow: wrapped value is 2^64 too big, 2^64 = EPS
-    uint64_t t1 = (uint64_t)hl * (uint32_t)EPS;  // mul.wide.u32
-    uint64_t t2 = t0 + t1;
-    if (t2 < t0) t2 += EPS;                 // carry: cannot overflow again
-    return t2;
+    return reduce_words((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) { return reduce128(a * b, __umul64hi(a, b)); }
+// 64 x 64 -> 128 as four IMAD.WIDE.U32 (the only multiplier shape the sm_100 fma-heavy pipe has for integers: 32
+// lanes/clk/SM) and five carry adds, then reduce_words.  "any" in, "any" out.
+__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
+    uint32_t z0, z1, z2, z3;
+    asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 q0, q1, m0, m1, h0, h1;\n\t"
+        "mul.wide.u32 p00, %4, %6;\n\t"
+        "mul.wide.u32 p01, %4, %7;\n\t"
+        "mul.wide.u32 p10, %5, %6;\n\t"
+        "mul.wide.u32 p11, %5, %7;\n\t"
+        "mov.b64 {%0, %1}, p00;\n\t"
+        "mov.b64 {q0, q1}, p01;\n\t"
+        "mov.b64 {m0, m1}, p10;\n\t"
+        "mov.b64 {h0, h1}, p11;\n\t"
+        "add.cc.u32  %1, %1, q0;\n\t"
+        "addc.cc.u32 %2, h0, q1;\n\t"
+        "addc.u32    %3, h1, 0;\n\t"
+        "add.cc.u32  %1, %1, m0;\n\t"
+        "addc.cc.u32 %2, %2, m1;\n\t"
+        "addc.u32    %3, %3, 0;\n\t"
+        "}" : "=&r"(z0), "=&r"(z1), "=&r"(z2), "=&r"(z3)
+            : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+    return reduce_words(z0, z1, z2, z3);
+}
 __device__ __forceinline__ uint64_t sqr(uint64_t a) { return mul(a, a); }
 __device__ __forceinline__ uint64_t mulc(uint64_t a, uint64_t b) { return canon(mul(a, b)); }
 

@@ -4,12 +4,16 @@
 // (semantics SURVEY.md A.5).  Pinned by the known-answer vectors found at
 // /root/reference/src/common/poseidon2/poseidon2_goldilocks.rs:190-211 (tests/golden/poseidon_kat.json).
 //
-// Formulation chosen for the 32-bit integer pipe:
-//   * state = 12 x u64 in registers, kept in "any" (non-canonical) form between layers;
-//   * S-box x^7 = 2 squarings + 2 multiplies, each 64x64->128 (4 IMAD.WIDE.U32) + reduce128;
-//   * MDS layer on the 32-bit halves of every lane: 2 x 144 small-constant IMAD.WIDE.U32 accumulations
-//     (sums stay below 2^42), recombined once per lane; the NEXT round's constant is folded into the accumulator
-//     initial value so there is no separate constant layer.
+// Formulation.  Measured on B200 (tools/ubench.cu): IMAD.WIDE.U32 issues at 32 lanes/clk/SM (fma-heavy
+// only), IADD3/LOP3/SHF at 64, DFMA/DADD at 64 on a pipe of their own, and the scheduler sustains ~120 warp-lanes/clk/SM
+// across the three.  So the permutation is split over all three pipes and written for the lowest instruction count:
+//   * S-box x^7 = 4 multiplies (gl::mul: 4 IMAD.WIDE.U32 + carry chains in PTX) on the fma + alu pipes;
+//   * the MDS layer runs on the fp64 pipe.  Each 64-bit lane is cut into two 32-bit limbs; a limb becomes a double for
+//     free (register pair {limb, 0x43300000} is the double 2^52 + limb), every sum of the layer stays below 2^53 and is
+//     therefore exact, and the results are read back from the mantissa bits.  The circulant is evaluated as a length-12
+//     cyclic convolution split by x^12-1 = (x^3-1)(x^3+1)(x^6+1): 103 DFMA/DADD per limb instead of 146 (plonky2 chose
+//     the matrix so that every folded constant is an integer — tools/mds_model.py);
+//   * the next round's constants ride in the accumulator initial values (POSEIDON_MDS_K), so there is no constant layer.
 #pragma once
 #include "gl_field.cuh"
 #include "poseidon_constants.cuh"
@@ -22,21 +26,6 @@ constexpr int N_FULL_HALF = 4;
 constexpr int N_PARTIAL = 22;
 constexpr int N_ROUNDS = 30;
 
-// circulant first row and diagonal (plonky2 hash/poseidon_goldilocks.rs · MDS_MATRIX_CIRC / MDS_MATRIX_DIAG)
-#define PSD_C0 17u
-#define PSD_C1 15u
-#define PSD_C2 41u
-#define PSD_C3 16u
-#define PSD_C4 2u
-#define PSD_C5 28u
-#define PSD_C6 13u
-#define PSD_C7 13u
-#define PSD_C8 39u
-#define PSD_C9 18u
-#define PSD_C10 34u
-#define PSD_C11 20u
-#define PSD_DIAG0 8u
-
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
     uint64_t x2 = gl::sqr(x);
     uint64_t x4 = gl::sqr(x2);
@@ -44,43 +33,96 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
     return gl::mul(x3, x4);
 }
 
-// out[r] = sum_i s[(i+r)%12]*C[i] + (r==0)*8*s[0] + rc[r]   (mod p), inputs "any", outputs "any".
-// rc == nullptr -> no constant.
-template <bool HAS_RC>
-__device__ __forceinline__ void mds_layer(uint64_t (&s)[WIDTH], const uint64_t* __restrict__ rc) {
-    constexpr uint32_t C[WIDTH] = {PSD_C0, PSD_C1, PSD_C2, PSD_C3, PSD_C4, PSD_C5,
-                                   PSD_C6, PSD_C7, PSD_C8, PSD_C9, PSD_C10, PSD_C11};
-    uint32_t lo[WIDTH], hi[WIDTH];
+constexpr double TWO52 = 4503599627370496.0;
+
+// exact integer value of a 32-bit word as a double: {w, 0x43300000} is 2^52 + w
+__device__ __forceinline__ double limb_to_double(uint32_t w) { return __dsub_rn(__hiloint2double(0x43300000, (int)w), TWO52); }
+
+// One limb of the MDS layer.  s[12]: exact integers (|s| < 2^35); k[12]: folded constants (uu0..2, uv0..2, v0..5);
+// o[r] = sum_i s[(i+r)%12]*CIRC[i] + (r==0)*8*s[0] + c[r], with c (and the 2^52 read-out bias) folded into k.
+// Mirrors tools/mds_model.py · mds_limb operation by operation.
+__device__ __forceinline__ void mds_limb(const double (&s)[WIDTH], const double* __restrict__ k, double (&o)[WIDTH]) {
+    double sp[6], sm[6];
 #pragma unroll
-    for (int i = 0; i < WIDTH; i++) {
-        lo[i] = (uint32_t)s[i];
-        hi[i] = (uint32_t)(s[i] >> 32);
+    for (int i = 0; i < 6; i++) {
+        sp[i] = __dadd_rn(s[i], s[i + 6]);
+        sm[i] = __dsub_rn(s[i], s[i + 6]);
     }
+    double a[3], b[3];
 #pragma unroll
-    for (int r = 0; r < WIDTH; r++) {
-        uint64_t al = 0, ah = 0;
-        if (HAS_RC) {
-            uint64_t k = rc[r];
-            al = (uint32_t)k;
-            ah = k >> 32;
-        }
-#pragma unroll
-        for (int i = 0; i < WIDTH; i++) {
-            al += (uint64_t)lo[(i + r) % WIDTH] * C[i];
-            ah += (uint64_t)hi[(i + r) % WIDTH] * C[i];
-        }
-        if (r == 0) {
-            al += (uint64_t)lo[0] * PSD_DIAG0;
-            ah += (uint64_t)hi[0] * PSD_DIAG0;
-        }
-        // value = al + ah*2^32,  al, ah < 2^42.   ah*2^32 = (ah_lo << 32) + ah_hi * 2^64,  2^64 = EPS
-        uint64_t x = al + ((uint64_t)(uint32_t)ah << 32);
-        uint32_t top = (uint32_t)(ah >> 32) + (x < al ? 1u : 0u);   // multiples of 2^64, < 2^11
-        uint64_t y = (uint64_t)top * (uint32_t)gl::EPS;
-        uint64_t z = x + y;
-        if (z < x) z += gl::EPS;   // wrapped z < 2^43, cannot overflow again
-        s[r] = z;
+    for (int i = 0; i < 3; i++) {
+        a[i] = __dadd_rn(sp[i], sp[i + 3]);
+        b[i] = __dsub_rn(sp[i], sp[i + 3]);
     }
+    // cyclic-3 with [16, 32, 16]:  UU[j] = 16*(a0 + a1 + a2) + 16*a[(j+2)%3]
+    const double S = __dadd_rn(__dadd_rn(a[0], a[1]), a[2]);
+    double U[6], V[6];
+    {
+        double UU[3], UV[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) UU[j] = __fma_rn(a[(j + 2) % 3], 16.0, __fma_rn(S, 16.0, k[j]));
+        // negacyclic-3 with [-1, -8, 2]
+        UV[0] = __fma_rn(b[2], 8.0, __fma_rn(b[1], -2.0, __dsub_rn(k[3], b[0])));
+        UV[1] = __fma_rn(b[2], -2.0, __fma_rn(b[0], -8.0, __dsub_rn(k[4], b[1])));
+        UV[2] = __fma_rn(b[1], -8.0, __fma_rn(b[0], 2.0, __dsub_rn(k[5], b[2])));
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            U[j] = __dadd_rn(UU[j], UV[j]);
+            U[j + 3] = __dsub_rn(UU[j], UV[j]);
+        }
+    }
+    // negacyclic-6 with f = [2, -4, 16, 1, -1, -1]:  V[n] = sum_{j<=n} sm[j] f[n-j] - sum_{j>n} sm[j] f[6+n-j]
+    constexpr double f[6] = {2.0, -4.0, 16.0, 1.0, -1.0, -1.0};
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+        double acc = k[6 + n];
+#pragma unroll
+        for (int j = 0; j < 6; j++) acc = __fma_rn(sm[j], (j <= n) ? f[n - j] : -f[6 + n - j], acc);
+        V[n] = acc;
+    }
+    // diagonal 8*s[0] reaches o[0] = U0 + V0 but not o[6] = U0 - V0
+    U[0] = __fma_rn(s[0], 4.0, U[0]);
+    V[0] = __fma_rn(s[0], 4.0, V[0]);
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+        o[n] = __dadd_rn(U[n], V[n]);
+        o[n + 6] = __dsub_rn(U[n], V[n]);
+    }
+}
+
+// (2^52 + al, 2^52 + ah) -> the 64-bit "any" word congruent to al + ah*2^32 (al, ah < 2^52; here < 2^43).
+// With a1 = al >> 32, b1 = ah >> 32:  al + ah*2^32 = a0 + (a1 + b1 + b0)*2^32 + b1*(2^64 - 2^32), and 2^64 = 2^32 - 1
+// turns the last term into -b1; the single possible carry k out of the middle word is folded the same way.  No
+// conditional fix-up is needed (tools/word_model.py · recombine_model).
+__device__ __forceinline__ uint64_t recombine(double AL, double AH) {
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u32 u, b1, T, g;\n\t"
+        "sub.u32     b1, %5, 0x43300000;\n\t"
+        "add.u32     u, %3, b1;\n\t"
+        "sub.u32     u, u, 0x43300000;\n\t"
+        "add.cc.u32  g, u, %4;\n\t"
+        "addc.u32    T, b1, 0;\n\t"
+        "addc.u32    g, g, 0;\n\t"
+        "sub.cc.u32  %0, %2, T;\n\t"
+        "subc.u32    %1, g, 0;\n\t"
+        "}" : "=&r"(lo), "=&r"(hi)
+            : "r"((uint32_t)__double2loint(AL)), "r"((uint32_t)__double2hiint(AL)), "r"((uint32_t)__double2loint(AH)),
+              "r"((uint32_t)__double2hiint(AH)));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// s <- MDS * s + (constants of layer `layer`)   — "any" in, "any" out
+__device__ __forceinline__ void mds_layer(uint64_t (&s)[WIDTH], int layer) {
+    const double* __restrict__ k = POSEIDON_MDS_K[layer];
+    double in[WIDTH], AL[WIDTH], AH[WIDTH];
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) in[i] = limb_to_double((uint32_t)s[i]);
+    mds_limb(in, k, AL);
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) in[i] = limb_to_double((uint32_t)(s[i] >> 32));
+    mds_limb(in, k + WIDTH, AH);
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) s[i] = recombine(AL[i], AH[i]);
 }
 
 // Full permutation. in/out "any" -> "any" (callers canonicalise what they store).
@@ -88,27 +130,15 @@ __device__ __forceinline__ void permute(uint64_t (&s)[WIDTH]) {
     // round-0 constants (all later constant layers are folded into the preceding MDS layer)
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = gl::add_any_c(s[i], POSEIDON_RC[i]);
-    int r = 0;
 #pragma unroll 1
-    for (; r < N_FULL_HALF; r++) {
-#pragma unroll
-        for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
-        mds_layer<true>(s, &POSEIDON_RC[WIDTH * (r + 1)]);
-    }
-#pragma unroll 1
-    for (; r < N_FULL_HALF + N_PARTIAL; r++) {
+    for (int r = 0; r < N_ROUNDS; r++) {
         s[0] = sbox7(s[0]);
-        mds_layer<true>(s, &POSEIDON_RC[WIDTH * (r + 1)]);
-    }
-#pragma unroll 1
-    for (; r < N_ROUNDS - 1; r++) {
+        if (r < N_FULL_HALF || r >= N_FULL_HALF + N_PARTIAL) {
 #pragma unroll
-        for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
-        mds_layer<true>(s, &POSEIDON_RC[WIDTH * (r + 1)]);
+            for (int i = 1; i < WIDTH; i++) s[i] = sbox7(s[i]);
+        }
+        mds_layer(s, r);
     }
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
-    mds_layer<false>(s, nullptr);
 }
 
 }  // namespace poseidon
