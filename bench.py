@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""Headline benchmark: PolynomialBatch commit throughput (iNTT + coset LDE + bit-reversed row-major leaves + Poseidon
+Merkle tree to the cap) on N B200s, in Melem/s (= N_rows * n_cols input elements per second), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one whole commit of the workload (default 2^20 x 135, rate_bits 3, cap_height 4 = BASELINE.json configs[2],
+the shape the metric is quoted on; it fits one GPU).  `value` is measured with the columns already resident in HBM
+(gl_dev_commit / the sharded device path), `e2e` through the reference-facing C ABI call gl_commit with host buffers
+(pinned), i.e. including the host->device copy of the inputs and the device->host read of the Merkle cap, every step.
+
+N > 1: the batch is sharded by polynomial column for the iNTT/LDE, exchanged column->row with one NCCL all-to-all, and
+every rank hashes whole cap subtrees of its contiguous leaf range; the subtree roots are all-gathered into the cap
+(SURVEY.md §8e).  Per-rank work shrinks with N ("strong" scaling of one commit).
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, C + OpenMP, all host threads) on a
+bounded sample of the same workload; the reference itself is Rust + an un-vendored crate and cannot be built here
+(DESIGN.md).  The oracle is used here only as the timed CPU baseline / checker, never on the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+P = 0xFFFF_FFFF_0000_0001
+METRIC = "commit Melem/s (2^20x135 LDE+Poseidon Merkle)"
+UNIT = "Melem/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--cols", type=int, default=135)
+    ap.add_argument("--rate-bits", type=int, default=3)
+    ap.add_argument("--cap-height", type=int, default=4)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=17, help="rows (log2) of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"PolynomialBatch::from_values commit 2^{a.log_n} x {a.cols}, rate_bits={a.rate_bits}, cap_height={a.cap_height}"
+
+
+def perms_per_commit(log_n, cols, r, h):
+    R = 1 << (log_n + r)
+    per_leaf = (cols + 7) // 8 if cols > 4 else 0
+    return R * per_leaf + (R - (1 << h))
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_commit_time(oc, log_n, cols, r, h, seed=1):
+    from oracle_c import splitmix_columns
+    x = splitmix_columns(seed, cols, 1 << log_n)
+    t = time.perf_counter()
+    res = oc.commit(x, r, min(h, log_n + r), want=())
+    return time.perf_counter() - t, res["stage_s"]
+
+
+def cpu_baseline(a, repeats=1):
+    from oracle_c import OracleC
+    oc = OracleC()
+    threads = oc.num_threads()
+    log_n = min(a.cpu_sample_log_n, a.log_n)
+    best, stages = None, None
+    for _ in range(repeats):
+        dt, st = cpu_commit_time(oc, log_n, a.cols, a.rate_bits, a.cap_height)
+        if best is None or dt < best:
+            best, stages = dt, st
+    return {"value": round((a.cols << log_n) / best / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one commit of 2^{log_n} x {a.cols} (rate_bits {a.rate_bits}, cap_height {a.cap_height}) = 1/{1 << (a.log_n - log_n)} of "
+                      f"the workload's rows, {best:.2f} s with {threads} OpenMP threads; oracle/gl_oracle.c (C restatement of the "
+                      "reference algorithm; the Rust reference cannot be built in this image)",
+            "stage_s": {k: round(v, 3) for k, v in zip(("ifft", "lde_fft", "transpose", "merkle"), stages)}}
+
+
+def run_reference(a):
+    """--impl reference: the CPU restatement on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle_c import OracleC
+    oc = OracleC()
+    threads = oc.num_threads()
+    log_n = min(a.cpu_sample_log_n, a.log_n)
+    for _ in range(a.warmup):
+        cpu_commit_time(oc, min(log_n, 12), a.cols, a.rate_bits, a.cap_height)     # warm-up on a small case (page-in, OpenMP pool)
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        cpu_commit_time(oc, log_n, a.cols, a.rate_bits, a.cap_height, seed=s + 1)
+    dt = time.perf_counter() - t0
+    val = a.steps * (a.cols << log_n) / dt / 1e6
+    sample = (f"each step = one commit of 2^{log_n} x {a.cols} (1/{1 << (a.log_n - log_n)} of the workload's rows; throughput in "
+              "elements/s is what is compared), oracle/gl_oracle.c with OpenMP")
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks field)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm = sorted(int(r[1]) for r in rows if r[1].isdigit())
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(rows[0][2]) if rows and rows[0][2].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max((float(r[3]) for r in rows if r[3].replace(".", "", 1).isdigit()), default=None)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def synth_columns(torch, dev, cols, n, seed):
+    """[cols][n] canonical Goldilocks words (SplitMix64 of the element index), generated on the device, int64 storage."""
+    idx = torch.arange(1, cols * n + 1, dtype=torch.int64, device=dev)
+    z = idx * -7046029254386353131 + (0x706C6F6E6B7932 ^ seed)                      # 0x9E3779B97F4A7C15 as int64
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * -4658895280553007687                  # 0xBF58476D1CE4E5B9
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * -7723592293110705685                  # 0x94D049BB133111EB
+    z = z ^ ((z >> 31) & ((1 << 33) - 1))
+    # unsigned z >= p  <=>  signed z in [-(2^32 - 1), -1]
+    z = torch.where((z < 0) & (z >= -(2**32 - 1)), z + (2**32 - 1), z)               # z - p (mod 2^64) = z + 2^32 - 1
+    return z.view(cols, n)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import plonky25_b200 as g
+    from plonky25_b200 import sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = g.Context(local)                      # raises without the CUDA library / a GPU: there is no fallback
+    lib = ctx.lib
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    log_n, cols, r, h = a.log_n, a.cols, a.rate_bits, a.cap_height
+    n = 1 << log_n
+    cap = np.zeros(4 << h, dtype=np.uint64)
+
+    if world == 1:
+        d_cols = synth_columns(torch, dev, cols, n, 1)
+        torch.cuda.synchronize()
+
+        def step():
+            hd = ctypes.c_uint64()
+            rc = lib.gl_dev_commit(ctx.handle, d_cols.data_ptr(), n, cols, log_n, r, h, 0, cap.ctypes.data, ctypes.byref(hd))
+            if rc != 0:
+                raise RuntimeError(lib.gl_ctx_last_error(ctx.handle).decode())
+            lib.gl_tree_free(ctx.handle, hd.value)
+    else:
+        plan = sharded.ShardPlan(cols, log_n, r, h, world)
+        c0, c1 = plan.col_range(rank)
+        d_cols = synth_columns(torch, dev, cols, n, 1)[c0:c1].contiguous()
+        state = sharded.ShardedCommit(ctx, plan, rank, dist, torch)
+        torch.cuda.synchronize()
+
+        def step():
+            cap[:] = state.commit(d_cols)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 0)):
+        step()
+    stage_acc = {}
+    launches = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(a.steps):
+        step()
+        ms, ln = ctx.stage_times()
+        for k, v in ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        launches += sum(ln.values())
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    dev_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+        tl = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(tl)
+        launches = int(tl.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = dev_ms / a.steps
+    value = cols * n / (ms_per_step * 1e-3) / 1e6
+    cap_dev = cap.copy()
+
+    # ---- e2e: the C-ABI call a Rust shim would make, host buffers in, cap out, every step --------------------------
+    e2e = None
+    if not a.no_e2e:
+        if world == 1:
+            host = ctypes.cast(lib.gl_host_alloc(cols * n * 8), ctypes.POINTER(ctypes.c_uint64))
+            if not host:
+                raise MemoryError("gl_host_alloc failed")
+            harr = np.ctypeslib.as_array(host, shape=(cols, n))
+            harr[:] = d_cols.cpu().numpy().view(np.uint64)
+            ptrs = (ctypes.c_void_p * cols)(*[harr[j].ctypes.data for j in range(cols)])
+
+            def e2e_step():
+                hd = ctypes.c_uint64()
+                rc = lib.gl_commit(ctx.handle, ptrs, cols, log_n, r, h, 0, None, None, None, cap.ctypes.data, ctypes.byref(hd))
+                if rc != 0:
+                    raise RuntimeError(lib.gl_ctx_last_error(ctx.handle).decode())
+                lib.gl_tree_free(ctx.handle, hd.value)
+            h2d = cols * n * 8
+        else:
+            harr = torch.empty((c1 - c0, n), dtype=torch.int64).pin_memory()
+            harr.copy_(d_cols)
+
+            def e2e_step():
+                d = harr.to(dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                cap[:] = state.commit(d)
+            h2d = (c1 - c0) * n * 8
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ta = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - ta
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
+            dist.all_reduce(hb)
+            h2d = int(hb.item())
+        assert np.array_equal(cap, cap_dev), "host-buffer path and device-resident path disagree on the Merkle cap"
+        e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
+               "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
+                      if world == 1 else "pinned host shard -> device, sharded commit, cap to host"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (leaf hashing), live CUDA-event time from the context's stage events -------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    R = n << r
+    rows_local = R // world
+    leaf_ms = stage_acc.get("leaf_hash", 0.0) / a.steps
+    alg_bytes = rows_local * (cols * 8 + 32)               # read every leaf word once, write one 32-byte digest per leaf
+    perms_leaf = rows_local * ((cols + 7) // 8)
+    roof = None
+    if leaf_ms > 0:
+        ach = alg_bytes / (leaf_ms * 1e-3) / 1e9
+        int_peak = None
+        try:
+            int_peak = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+        except OSError:
+            pass
+        roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": round(ach, 2), "peak": peak_gbs, "unit": "GB/s",
+                "frac": round(ach / peak_gbs, 5), "traffic": None, "peak_source": peak_src, "ms_per_launch": round(leaf_ms, 3),
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "hashing is bound by the SM integer/fp64 issue rate, not HBM (DESIGN.md §roofline): see int_pipe",
+                "int_pipe": {"permutations_per_s": round(perms_leaf / (leaf_ms * 1e-3), 1),
+                             "peak_permutations_per_s": (int_peak or {}).get("poseidon_perm_issue_bound_per_s"),
+                             "frac": (round(perms_leaf / (leaf_ms * 1e-3) / int_peak["poseidon_perm_issue_bound_per_s"], 4)
+                                      if int_peak and int_peak.get("poseidon_perm_issue_bound_per_s") else None)}}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "leaf_hash_traffic.json")))
+            if prof.get("rows") == rows_local and prof.get("cols") == cols:
+                roof["traffic"] = prof["dram_bytes_per_launch"]
+        except OSError:
+            pass
+
+    cpu = None if a.no_cpu_baseline else cpu_baseline(a)
+
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "log_n": log_n, "n_cols": cols, "rate_bits": r, "cap_height": h,
+                       "sharding": "none" if world == 1 else f"columns/{world} -> all-to-all -> leaf ranges/{world}",
+                       "l2": "inputs (%.2f GB) and leaves (%.2f GB) exceed the 126 MB L2; no flush needed" % (cols * n * 8 / 1e9, R * cols * 8 / 1e9),
+                       "permutations_per_step": perms_per_commit(log_n, cols, r, h)},
+            "stage_ms": {k: round(v / a.steps, 4) for k, v in stage_acc.items()},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,12 +118,13 @@ int gl_poseidon_permute(gl_ctx* ctx, uint64_t* states, uint64_t n);
 int gl_dev_commit(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
                   uint32_t rate_bits, uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_batch);
 /* stage 1 of the sharded commit: iNTT + coset LDE of a column shard; d_out_rows = [R][out_pitch] row-major
- * (out_pitch multiple of 8), rows in bit-reversed LDE order; d_out_coeffs = [N][out_pitch] or NULL              */
+ * (out_pitch multiple of 4), rows in bit-reversed LDE order; d_out_coeffs = [N][out_pitch] or NULL              */
 int gl_dev_lde(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
                uint32_t rate_bits, int input_is_coeffs, uint64_t* d_out_rows, uint32_t out_pitch,
                uint64_t* d_out_coeffs);
-/* copy a received [n_rows][src_cols] block into columns [dst_col_off, dst_col_off+src_cols) of [n_rows][dst_pitch] */
-int gl_dev_repack(gl_ctx* ctx, const uint64_t* d_src, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,
+/* copy the first src_cols columns of a received [n_rows][src_pitch] block into columns
+ * [dst_col_off, dst_col_off+src_cols) of [n_rows][dst_pitch] (canonicalising) */
+int gl_dev_repack(gl_ctx* ctx, const uint64_t* d_src, uint32_t src_pitch, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,
                   uint32_t dst_pitch, uint32_t dst_col_off);
 /* stage 3: Merkle subtrees over device rows [n_leaves][pitch]; d_digests 2*(n_leaves-2^cap_height)*4 words (device),
  * out_cap host 2^cap_height*4 */

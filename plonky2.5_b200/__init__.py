@@ -6,6 +6,7 @@ include/gl_commit.h.  The directory name contains a dot, so import it as ``plonk
 repository root) or via importlib.
 """
 from . import _lib  # noqa: F401
+from . import sharded  # noqa: F401
 from .api import (Challenger, Context, FriParams, GlError, MerkleCap, MerkleTree, PolynomialBatch,  # noqa: F401
                   default_context, fri_committed_trees)
 from .build import build  # noqa: F401

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -42,17 +43,59 @@ struct GlError {
         }                                                                                                  \
     } while (0)
 
+// Device allocations are recycled through a small per-process free list: a commit needs ~11 GB of leaves/digests at
+// 2^20 x 135 and cudaMalloc/cudaFree of that size is milliseconds of driver time per call.  Exact-size reuse only.
+struct DevPool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, uint64_t*> free_list;   // (device, words) -> pointer
+    size_t cached_words = 0;
+    static DevPool& get() { static DevPool p; return p; }
+    uint64_t* take(int dev, size_t words) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_list.find({dev, words});
+        if (it == free_list.end()) return nullptr;
+        uint64_t* p = it->second;
+        free_list.erase(it);
+        cached_words -= words;
+        return p;
+    }
+    void give(int dev, size_t words, uint64_t* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        free_list.insert({{dev, words}, p});
+        cached_words += words;
+    }
+    void trim(int dev) {   // release everything cached for `dev` (on allocation failure / context destruction)
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto it = free_list.begin(); it != free_list.end();) {
+            if (it->first.first == dev) { cudaFree(it->second); cached_words -= it->first.second; it = free_list.erase(it); }
+            else ++it;
+        }
+    }
+};
+
 struct DevBuf {
     uint64_t* p = nullptr;
     size_t words = 0;
+    int dev = -1;
     void ensure(size_t w) {
         if (w <= words) return;
         release();
-        CUDA_CHECK(cudaMalloc(&p, (w ? w : 1) * sizeof(uint64_t)));
+        if (w == 0) w = 1;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        p = DevPool::get().take(dev, w);
+        if (!p) {
+            cudaError_t e = cudaMalloc(&p, w * sizeof(uint64_t));
+            if (e == cudaErrorMemoryAllocation) {   // give cached blocks back to the driver and retry once
+                cudaGetLastError();
+                DevPool::get().trim(dev);
+                e = cudaMalloc(&p, w * sizeof(uint64_t));
+            }
+            if (e != cudaSuccess) { p = nullptr; CUDA_CHECK(e); }
+        }
         words = w;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) DevPool::get().give(dev, words, p);
         p = nullptr;
         words = 0;
     }
@@ -287,7 +330,10 @@ void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream))
 void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
                int is_coeffs, uint64_t* d_coeffs, uint32_t coeff_pitch, uint64_t* d_rows, uint32_t row_pitch, bool timed) {
     const uint64_t N = 1ULL << log_n;
-    const uint32_t cols_padded = round_up(n_cols, 8);
+    // column groups of 8 words (64 B row segments); a narrow shard whose padding to 8 would waste >= 4 columns runs
+    // in groups of 4 (32 B = one sector) instead
+    const int G = (round_up(n_cols, 8) - n_cols >= 4 && coeff_pitch % 4 == 0 && row_pitch % 4 == 0) ? 4 : 8;
+    const uint32_t cols_padded = round_up(n_cols, G);
     dim3 tb(32, 8);
     dim3 tg((uint32_t)((N + 31) / 32), (coeff_pitch + 31) / 32);
     uint32_t* l_tr = timed ? &c->launches[GL_STAGE_TRANSPOSE] : nullptr;
@@ -304,13 +350,13 @@ void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
         CUDA_CHECK(cudaGetLastError());
         if (l_tr) (*l_tr)++;
         if (timed) record(c, GL_STAGE_INTT);
-        run_ntt(c, c->vals.p, coeff_pitch, d_coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, 8, l_in);
+        run_ntt(c, c->vals.p, coeff_pitch, d_coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, G, l_in);
     }
     if (timed) record(c, GL_STAGE_LDE);
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
     for (uint32_t s = 0; s < (1u << rate_bits); s++) {
         uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch;
-        run_ntt(c, d_coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], 8, l_ld);
+        run_ntt(c, d_coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
     }
 }
 
@@ -442,6 +488,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->roots.clear();
     c->lde_tables.clear();
     c->in_stage.release(); c->vals.release(); c->scratch.release();
+    DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -474,22 +521,29 @@ int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
     GL_API_BEGIN(c)
     check_shape(n_cols, log_n, rate_bits, 0);
     if (!d_cols || !d_out_rows) GL_THROW(GL_ERR_INVALID, "NULL device pointer");
-    if (out_pitch % 8 || out_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "out_pitch must be a multiple of 8 and >= n_cols");
+    if (out_pitch % 4 || out_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "out_pitch must be a multiple of 4 and >= n_cols");
     uint64_t* coeffs = d_out_coeffs;
     if (!coeffs) { c->scratch.ensure(((uint64_t)1 << log_n) * out_pitch); coeffs = c->scratch.p; }
-    lde_stage(c, d_cols, col_stride, n_cols, log_n, rate_bits, input_is_coeffs, coeffs, out_pitch, d_out_rows, out_pitch, false);
+    get_roots(c, log_n);
+    get_lde_tables(c, log_n, rate_bits);
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+    record(c, GL_STAGE_TRANSPOSE);
+    lde_stage(c, d_cols, col_stride, n_cols, log_n, rate_bits, input_is_coeffs, coeffs, out_pitch, d_out_rows, out_pitch, true);
+    record(c, GL_STAGE_LEAF_HASH);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
+        CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     return GL_OK;
     GL_API_END(c)
 }
 
-int gl_dev_repack(gl_ctx* c, const uint64_t* d_src, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst, uint32_t dst_pitch,
-                  uint32_t dst_col_off) {
+int gl_dev_repack(gl_ctx* c, const uint64_t* d_src, uint32_t src_pitch, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,
+                  uint32_t dst_pitch, uint32_t dst_col_off) {
     GL_API_BEGIN(c)
-    if (!d_src || !d_dst || dst_col_off + src_cols > dst_pitch) GL_THROW(GL_ERR_INVALID, "bad repack arguments");
+    if (!d_src || !d_dst || dst_col_off + src_cols > dst_pitch || src_cols > src_pitch) GL_THROW(GL_ERR_INVALID, "bad repack arguments");
     uint64_t total = n_rows * src_cols;
     if (total) {
-        ntt::repitch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(d_src, src_cols, d_dst, dst_pitch, dst_col_off,
+        ntt::repitch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(d_src, src_pitch, d_dst, dst_pitch, dst_col_off,
                                                                                   src_cols, n_rows);
         CUDA_CHECK(cudaGetLastError());
     }
@@ -507,9 +561,15 @@ int gl_dev_merkle(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32
     if (pitch % 8 || pitch < leaf_len) GL_THROW(GL_ERR_INVALID, "pitch must be a multiple of 8 and >= leaf_len");
     if (!d_digests && n_leaves > (1ULL << cap_height)) GL_THROW(GL_ERR_INVALID, "d_digests is NULL");
     c->scratch.ensure(4ULL << cap_height);
-    merkle_build(c, d_leaves, n_leaves, leaf_len, pitch, cap_height, d_digests, c->scratch.p, nullptr, nullptr, nullptr);
+    for (int i : {GL_STAGE_LEAF_HASH, GL_STAGE_TREE, GL_STAGE_D2H}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+    record(c, GL_STAGE_LEAF_HASH);
+    merkle_build(c, d_leaves, n_leaves, leaf_len, pitch, cap_height, d_digests, c->scratch.p, &c->launches[GL_STAGE_LEAF_HASH],
+                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    record(c, GL_STAGE_D2H);
     CUDA_CHECK(cudaMemcpyAsync(out_cap, c->scratch.p, 32ULL << cap_height, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i : {GL_STAGE_LEAF_HASH, GL_STAGE_TREE})
+        CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     return GL_OK;
     GL_API_END(c)
 }

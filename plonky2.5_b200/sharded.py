@@ -1,0 +1,122 @@
+"""Multi-GPU commit: one process per GPU, sharded by polynomial column, exchanged column->row, hashed by leaf range.
+
+SURVEY.md §8(e) / BASELINE.json north_star:
+  1. rank g runs the iNTT + coset LDE of its column slice  (gl_dev_lde; columns are independent polynomials);
+  2. one all-to-all turns column slices into row slices: rank q receives, from every rank, the rows of its contiguous
+     leaf range  [q*R/G, (q+1)*R/G)  — whole cap subtrees, because 2^cap_height >= G;
+  3. rank q hashes its leaves and builds its 2^cap_height/G subtrees (gl_dev_merkle); the local digest buffer is exactly
+     this rank's slice of plonky2's `digests` vector;
+  4. the subtree roots are all-gathered into the MerkleCap.
+
+`ShardPlan` is pure host arithmetic (tested on CPU with gloo, world_size 2); `ShardedCommit` needs CUDA + NCCL.
+torch.distributed is plumbing only: the exchange is `all_to_all_single` on device buffers the library filled.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Tuple
+
+import numpy as np
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class ShardPlan:
+    """Who owns which columns (LDE stage) and which leaf rows (Merkle stage), and the all-to-all split sizes."""
+
+    def __init__(self, n_cols: int, log_n: int, rate_bits: int, cap_height: int, world: int):
+        if world < 1 or world & (world - 1):
+            raise ValueError("world size must be a power of two")
+        if (1 << cap_height) < world:
+            raise ValueError("cap_height too small: every rank must own at least one whole cap subtree")
+        if n_cols < world:
+            raise ValueError("fewer columns than ranks")
+        self.n_cols, self.log_n, self.rate_bits, self.cap_height, self.world = n_cols, log_n, rate_bits, cap_height, world
+        self.n_rows = 1 << (log_n + rate_bits)               # R
+        self.rows_per_rank = self.n_rows // world
+        self.local_cap_height = cap_height - (world.bit_length() - 1)
+        base, rem = divmod(n_cols, world)
+        self.col_counts = [base + (1 if g < rem else 0) for g in range(world)]
+        self.col_offsets = [sum(self.col_counts[:g]) for g in range(world)]
+        # device pitch of a rank's LDE output: multiple of 4 words (see gl_dev_lde), of 8 when that wastes < 4 columns
+        self.pitches = [_round_up(c, 8) if _round_up(c, 8) - c < 4 else _round_up(c, 4) for c in self.col_counts]
+        self.leaf_pitch = _round_up(n_cols, 8)
+
+    def col_range(self, rank: int) -> Tuple[int, int]:
+        return self.col_offsets[rank], self.col_offsets[rank] + self.col_counts[rank]
+
+    def row_range(self, rank: int) -> Tuple[int, int]:
+        return rank * self.rows_per_rank, (rank + 1) * self.rows_per_rank
+
+    def send_splits(self, rank: int) -> List[int]:
+        """words sent by `rank` to each peer: its rows_per_rank x pitch[rank] slab of that peer's leaf range"""
+        return [self.rows_per_rank * self.pitches[rank]] * self.world
+
+    def recv_splits(self, rank: int) -> List[int]:
+        return [self.rows_per_rank * self.pitches[q] for q in range(self.world)]
+
+    def digests_per_rank(self) -> int:
+        return 2 * (self.rows_per_rank - (1 << self.local_cap_height))
+
+    def exchange_bytes_per_rank(self) -> int:
+        """algorithmic bytes a rank sends to OTHER ranks (8*C_g*R*(G-1)/G)"""
+        return 8 * self.rows_per_rank * (self.world - 1) * max(self.col_counts)
+
+
+def exchange_reference(plan: ShardPlan, shards: List[np.ndarray]) -> List[np.ndarray]:
+    """Host model of step 2 for tests: shards[g] is rank g's [R][pitch_g] LDE output; returns each rank's [R/G][n_cols] leaves."""
+    out = []
+    for q in range(plan.world):
+        r0, r1 = plan.row_range(q)
+        out.append(np.concatenate([shards[g][r0:r1, :plan.col_counts[g]] for g in range(plan.world)], axis=1))
+    return out
+
+
+class ShardedCommit:
+    """Device buffers + the four steps above for one rank.  Buffers are allocated once and reused by every commit."""
+
+    def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch):
+        self.ctx, self.plan, self.rank, self.dist, self.torch = ctx, plan, rank, dist, torch
+        dev = torch.device("cuda", ctx.device)
+        p = plan
+        i64 = torch.int64
+        self.rows = torch.empty(p.n_rows * p.pitches[rank], dtype=i64, device=dev)          # [R][pitch_g]
+        self.coeffs = torch.empty((1 << p.log_n) * p.pitches[rank], dtype=i64, device=dev)  # [N][pitch_g]
+        self.recv = torch.empty(sum(p.recv_splits(rank)), dtype=i64, device=dev)
+        self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=i64, device=dev)    # [R/G][leaf_pitch]
+        self.digests = torch.empty(max(p.digests_per_rank() * 4, 1), dtype=i64, device=dev)
+        self.cap_local = np.zeros(4 << p.local_cap_height, dtype=np.uint64)
+        self.cap_dev = torch.empty(4 << p.local_cap_height, dtype=i64, device=dev)
+        self.cap_all = torch.empty(4 << p.cap_height, dtype=i64, device=dev)
+        self.exchange_ms = 0.0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.ctx.lib.gl_ctx_last_error(self.ctx.handle).decode())
+
+    def commit(self, d_cols) -> np.ndarray:
+        """d_cols: this rank's [n_cols_g][N] device tensor (column-major, int64 storage of u64 words).  Returns the full cap."""
+        p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
+        n = 1 << p.log_n
+        ncg = p.col_counts[self.rank]
+        assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
+        self._check(lib.gl_dev_lde(h, d_cols.data_ptr(), n, ncg, p.log_n, p.rate_bits, 0, self.rows.data_ptr(), p.pitches[self.rank],
+                                   self.coeffs.data_ptr()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.dist.all_to_all_single(self.recv, self.rows, p.recv_splits(self.rank), p.send_splits(self.rank))
+        e1.record()
+        torch.cuda.current_stream().synchronize()
+        self.exchange_ms = e0.elapsed_time(e1)
+        off = 0
+        for q in range(p.world):
+            self._check(lib.gl_dev_repack(h, self.recv.data_ptr() + 8 * off, p.pitches[q], p.col_counts[q], p.rows_per_rank,
+                                          self.leaves.data_ptr(), p.leaf_pitch, p.col_offsets[q]))
+            off += p.rows_per_rank * p.pitches[q]
+        self._check(lib.gl_dev_merkle(h, self.leaves.data_ptr(), p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
+                                      self.digests.data_ptr(), self.cap_local.ctypes.data))
+        self.cap_dev.copy_(torch.from_numpy(self.cap_local.view(np.int64)))
+        self.dist.all_gather_into_tensor(self.cap_all, self.cap_dev)
+        return self.cap_all.cpu().numpy().view(np.uint64)

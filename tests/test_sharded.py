@@ -1,0 +1,101 @@
+"""Host logic of the multi-GPU commit (plonky2.5_b200/sharded.py) on CPU: the shard plan, and the column->row exchange run
+for real over torch.distributed with the gloo backend at world_size 2 (the N>1 path's collective, without GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import plonky25_b200 as g
+from plonky25_b200.sharded import ShardPlan, exchange_reference
+
+
+def test_plan_partitions_cover_everything():
+    for (cols, log_n, r, h, world) in [(135, 20, 3, 4, 8), (135, 16, 3, 4, 4), (256, 22, 1, 4, 2), (20, 10, 3, 4, 16), (17, 8, 2, 1, 2)]:
+        p = ShardPlan(cols, log_n, r, h, world)
+        assert sum(p.col_counts) == cols and p.col_offsets[0] == 0
+        assert all(p.col_range(k)[1] == p.col_range(k + 1)[0] for k in range(world - 1))
+        assert max(p.col_counts) - min(p.col_counts) <= 1
+        assert p.rows_per_rank * world == 1 << (log_n + r)
+        assert (1 << p.local_cap_height) * world == 1 << h
+        assert all(pt % 4 == 0 and pt >= c and pt - c < 4 for pt, c in zip(p.pitches, p.col_counts))
+        # plonky2 digest layout: the global digests vector is the concatenation of the ranks' local vectors
+        assert p.digests_per_rank() * world == 2 * ((1 << (log_n + r)) - (1 << h))
+        for k in range(world):
+            assert sum(p.recv_splits(k)) == p.rows_per_rank * sum(p.pitches)
+            assert p.send_splits(k)[0] == p.recv_splits((k + 1) % world)[k]
+
+
+def test_plan_rejects_bad_shapes():
+    with pytest.raises(ValueError):
+        ShardPlan(135, 10, 3, 4, 3)
+    with pytest.raises(ValueError):
+        ShardPlan(135, 10, 3, 2, 8)      # 4 subtrees cannot be split over 8 ranks
+    with pytest.raises(ValueError):
+        ShardPlan(3, 10, 3, 4, 4)
+
+
+def _shard(plan, rank):
+    """synthetic 'LDE output' of a rank: value encodes (row, global column); padding columns hold a poison value"""
+    R, pt, c0 = plan.n_rows, plan.pitches[rank], plan.col_offsets[rank]
+    a = np.full((R, pt), -1, dtype=np.int64)
+    rows = np.arange(R, dtype=np.int64)[:, None]
+    a[:, :plan.col_counts[rank]] = rows * 1000 + c0 + np.arange(plan.col_counts[rank], dtype=np.int64)[None, :]
+    return a
+
+
+def _worker(rank, world, port, cols, log_n, r, h, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = ShardPlan(cols, log_n, r, h, world)
+        send = torch.from_numpy(_shard(plan, rank).reshape(-1))
+        recv = torch.empty(sum(plan.recv_splits(rank)), dtype=torch.int64)
+        dist.all_to_all_single(recv, send, plan.recv_splits(rank), plan.send_splits(rank))
+        leaves = np.zeros((plan.rows_per_rank, cols), dtype=np.int64)
+        off = 0
+        for src in range(world):                       # what gl_dev_repack does on the device
+            blk = recv[off:off + plan.rows_per_rank * plan.pitches[src]].numpy().reshape(plan.rows_per_rank, plan.pitches[src])
+            leaves[:, plan.col_offsets[src]:plan.col_offsets[src] + plan.col_counts[src]] = blk[:, :plan.col_counts[src]]
+            off += blk.size
+        r0, _ = plan.row_range(rank)
+        want = (np.arange(r0, r0 + plan.rows_per_rank, dtype=np.int64)[:, None] * 1000 + np.arange(cols, dtype=np.int64)[None, :])
+        ok = bool(np.array_equal(leaves, want))
+        # subtree-root gather
+        cap_local = torch.full((4 << plan.local_cap_height,), rank, dtype=torch.int64)
+        cap_all = [torch.empty_like(cap_local) for _ in range(world)]
+        dist.all_gather(cap_all, cap_local)
+        ok = ok and [int(c[0]) for c in cap_all] == list(range(world))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(135, 6, 3, 4), (19, 5, 1, 1)])
+def test_exchange_over_gloo_world2(shape):
+    import torch.multiprocessing as mp
+    cols, log_n, r, h = shape
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_worker, args=(k, 2, port, cols, log_n, r, h, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_exchange_reference_model():
+    plan = ShardPlan(37, 4, 2, 2, 4)
+    shards = [_shard(plan, k) for k in range(4)]
+    leaves = exchange_reference(plan, shards)
+    for k in range(4):
+        r0, _ = plan.row_range(k)
+        want = (np.arange(r0, r0 + plan.rows_per_rank, dtype=np.int64)[:, None] * 1000 + np.arange(37, dtype=np.int64)[None, :])
+        assert np.array_equal(leaves[k], want)
