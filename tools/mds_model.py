@@ -74,3 +74,171 @@ if __name__ == "__main__":
         lo, hi = rc_limbs(rc)
         assert (lo + (hi << 32)) % P == rc and lo % 4 == 0 and hi % 4 == 0
     print("mds model ok")
+
+
+# ======================================================================================================================
+# v3: lanes 1..11 stay in fp64 limbs through the 22 partial rounds
+# ======================================================================================================================
+N_ROUNDS, FULL_HALF, N_PARTIAL = 30, 4, 22
+BIAS = 1 << 52
+# positivity offsets for limbs that leave the fp64 pipe after having been signed:  OFF_LO + OFF_HI*2^32 = 2^17 * p
+OFF_LO = (1 << 49) + (1 << 17)
+OFF_HI = (1 << 49) - (1 << 18)
+assert OFF_LO + (OFF_HI << 32) == (1 << 17) * P and OFF_LO % 4 == 0 and OFF_HI % 4 == 0
+
+
+def mds_field(v):
+    return [x % P for x in mds_direct(v)]
+
+
+def partial_constants(rc):
+    """Push the lane 1..11 constants of partial rounds 5..25 forward through the MDS (sbox acts on lane 0 only, so
+    sigma0(s + e + d) = sigma0(s + e) + d for d with zero lane 0).  Returns (lane0[r] for r = 5..26, tail[1..11] added
+    before round 26's S-boxes)."""
+    cur = [rc[12 * 5 + i] for i in range(12)]
+    lane0 = {}
+    for r in range(5, 26):
+        lane0[r] = cur[0]
+        d = [0] + cur[1:]
+        nxt = mds_field(d)
+        cur = [(rc[12 * (r + 1) + i] + nxt[i]) % P for i in range(12)]
+    lane0[26] = cur[0]
+    return lane0, cur[1:]
+
+
+def check53(*vals):
+    for v in vals:
+        assert abs(v) < (1 << 53), "fp64 exactness bound violated: %d" % v
+
+
+def mds_limb_checked(s, k):
+    """mds_limb with the |x| < 2^53 check on every intermediate (all values are integers, so that is exactness)."""
+    sp = [s[i] + s[i + 6] for i in range(6)]; sm = [s[i] - s[i + 6] for i in range(6)]
+    a = [sp[i] + sp[i + 3] for i in range(3)]; b = [sp[i] - sp[i + 3] for i in range(3)]
+    S = a[0] + a[1] + a[2]
+    check53(*sp, *sm, *a, *b, S)
+    UU = []
+    for j in range(3):
+        t = S * 16 + k[j]; check53(t); u = a[(j + 2) % 3] * 16 + t; check53(u); UU.append(u)
+    UV = []
+    for (c0, c1, c2, kk) in ((-1, -2, 8, k[3]), (-8, -1, -2, k[4]), (2, -8, -1, k[5])):
+        t = kk
+        for coef, x in ((c0, b[0]), (c1, b[1]), (c2, b[2])):
+            t = t + coef * x; check53(t)
+        UV.append(t)
+    U = [UU[j] + UV[j] for j in range(3)] + [UU[j] - UV[j] for j in range(3)]
+    V = []
+    for n in range(6):
+        acc = k[6 + n]
+        for j in range(6):
+            acc += sm[j] * (F6[n - j] if j <= n else -F6[6 + n - j]); check53(acc)
+        V.append(acc)
+    U[0] += s[0] * 4; V[0] += s[0] * 4
+    o = [U[n] + V[n] for n in range(6)] + [U[n] - V[n] for n in range(6)]
+    check53(*U, *V, *o)
+    return o
+
+
+def rint_div(x, sh):
+    """round-to-nearest-even of x / 2^sh (what (x*2^-sh + 1.5*2^52) - 1.5*2^52 computes in fp64)"""
+    q, r = divmod(x, 1 << sh)
+    half = 1 << (sh - 1)
+    if r > half or (r == half and (q & 1)):
+        q += 1
+    return q
+
+
+def normalize(L, H):
+    cL = rint_div(L, 32); L1 = L - (cL << 32); H1 = H + cL
+    cH = rint_div(H1, 32); H2 = H1 - (cH << 32)
+    return L1 - cH, H2 + cH
+
+
+def sbox(x):
+    return pow(x, 7, P)
+
+
+def permute_v3(state, rc, stats=None):
+    """Mirror of csrc/poseidon.cuh · permute (v3) on exact integers."""
+    lane0_c, tail_c = partial_constants(rc)
+    s = [(state[i] + rc[i]) % P for i in range(12)]
+
+    def full_layer(s, r):
+        lanes = [rc[12 * (r + 1) + i] if r < 29 else 0 for i in range(12)]
+        limbs = [rc_limbs(c) for c in lanes]
+        out = []
+        for limb in (0, 1):
+            k = [int(x) for x in fold_constants([l[limb] + BIAS for l in limbs])]
+            ins = [(v >> (32 * limb)) & 0xFFFFFFFF for v in s]
+            o = mds_limb_checked(ins, k)
+            assert all(BIAS <= x < 2 * BIAS for x in o)
+            out.append([x - BIAS for x in o])
+        return [(out[0][i] + (out[1][i] << 32)) % P for i in range(12)]
+
+    for r in range(0, 4):
+        s = [sbox(x) for x in s]
+        s = full_layer(s, r)
+    x0 = s[0]
+    L = [v & 0xFFFFFFFF for v in s]; H = [v >> 32 for v in s]          # lanes 1..11 resident (index 0 unused)
+    for r in range(4, 26):
+        x0 = sbox(x0)
+        L[0], H[0] = x0 & 0xFFFFFFFF, x0 >> 32
+        c0 = lane0_c[r + 1]
+        cl, ch = rc_limbs(c0)
+        outs = []
+        for limb, ins, cc, off in ((0, L, cl, OFF_LO), (1, H, ch, OFF_HI)):
+            q = (cc + BIAS + off) // 4
+            assert (cc + BIAS + off) % 4 == 0
+            k = [q, 0, 0, q, 0, 0, 2 * q, 0, 0, 0, 0, 0]
+            o = mds_limb_checked(ins, k)
+            assert BIAS <= o[0] < 2 * BIAS, "lane 0 read-out out of the mantissa window"
+            outs.append(o)
+        x0 = ((outs[0][0] - BIAS) + ((outs[1][0] - BIAS) << 32)) % P       # recombine (offsets are = 0 mod p)
+        L, H = outs[0], outs[1]
+        if stats is not None:
+            stats["max_unnorm"] = max(stats.get("max_unnorm", 0), max(abs(v) for v in L[1:] + H[1:]))
+        if r & 1:
+            for i in range(1, 12):
+                L[i], H[i] = normalize(L[i], H[i])
+                assert abs(L[i]) <= (1 << 31) + (1 << 21) and abs(H[i]) <= (1 << 31) + (1 << 21)
+    # leave the fp64 domain: lanes 1..11 get tail constant + offset + bias, then recombine
+    s = [x0]
+    for i in range(1, 12):
+        cl, ch = rc_limbs(tail_c[i - 1])
+        al = L[i] + cl + OFF_LO + BIAS; ah = H[i] + ch + OFF_HI + BIAS
+        check53(al, ah)
+        assert BIAS <= al < 2 * BIAS and BIAS <= ah < 2 * BIAS
+        s.append(((al - BIAS) + ((ah - BIAS) << 32)) % P)
+    for r in range(26, 30):
+        s = [sbox(x) for x in s]
+        s = full_layer(s, r)
+    return s
+
+
+def permute_naive(state, rc):
+    s = list(state)
+    for r in range(30):
+        s = [(s[i] + rc[12 * r + i]) % P for i in range(12)]
+        if r < 4 or r >= 26:
+            s = [sbox(x) for x in s]
+        else:
+            s[0] = sbox(s[0])
+        s = mds_field(s)
+    return s
+
+
+def selftest_v3():
+    import os, sys, random
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from gen_poseidon_constants import constants
+    rc = constants()
+    rnd = random.Random(5)
+    stats = {}
+    tests = [[0] * 12, list(range(12)), [P - 1] * 12] + [[rnd.randrange(P) for _ in range(12)] for _ in range(40)]
+    for st in tests:
+        assert permute_v3(st, rc, stats) == permute_naive(st, rc)
+    print("permute_v3 model ok; max |unnormalised resident limb| = 2^%.2f" % (stats["max_unnorm"].bit_length()))
+
+
+if __name__ == "__main__":
+    selftest_v3()
