@@ -47,9 +47,8 @@ __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
 }
 
 // 64 x 64 -> 128 as four IMAD.WIDE.U32 (the only multiplier shape the sm_100 fma-heavy pipe has for integers: 32
-// lanes/clk/SM) and five carry adds, then reduce_words.  "any" in, "any" out.
-__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
-    uint32_t z0, z1, z2, z3;
+// lanes/clk/SM) and five carry adds: (z3:z2:z1:z0) = a * b.
+__device__ __forceinline__ void mul_words(uint64_t a, uint64_t b, uint32_t& z0, uint32_t& z1, uint32_t& z2, uint32_t& z3) {
     asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 q0, q1, m0, m1, h0, h1;\n\t"
         "mul.wide.u32 p00, %4, %6;\n\t"
         "mul.wide.u32 p01, %4, %7;\n\t"
@@ -67,6 +66,11 @@ __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
         "addc.u32    %3, %3, 0;\n\t"
         "}" : "=&r"(z0), "=&r"(z1), "=&r"(z2), "=&r"(z3)
             : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+}
+// "any" in, "any" out
+__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
+    uint32_t z0, z1, z2, z3;
+    mul_words(a, b, z0, z1, z2, z3);
     return reduce_words(z0, z1, z2, z3);
 }
 __device__ __forceinline__ uint64_t sqr(uint64_t a) { return mul(a, a); }

@@ -35,10 +35,26 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
 
 constexpr double TWO52 = 4503599627370496.0;
 
-// exact integer value of a 32-bit word as a double: {w, 0x43300000} is 2^52 + w
-__device__ __forceinline__ double limb_to_double(uint32_t w) { return __dsub_rn(__hiloint2double(0x43300000, (int)w), TWO52); }
+// {w, 0x43300000} is the double 2^52 + w
+__device__ __forceinline__ double biased(uint32_t w) { return __hiloint2double(0x43300000, (int)w); }
+// exact integer value of a 32-bit word as a double
+__device__ __forceinline__ double limb_to_double(uint32_t w) { return __dsub_rn(biased(w), TWO52); }
 
-// One limb of the MDS layer.  s[12]: exact integers (|s| < 2^35); k[12]: folded constants (uu0..2, uv0..2, v0..5);
+// x^7 handed to the fp64 MDS as two limbs (value = lo + hi*2^32 mod p).  The last product x^3 * x^4 = (z3:z2:z1:z0) is
+// not reduced to 64 bits on the integer pipe: 2^64 = 2^32 - 1 and 2^96 = -1 give lo = z0 - z2 - z3 (signed, |lo| < 2^33)
+// and hi = z1 + z2 (< 2^33), six exact DADDs — cheaper than reduce_words + conversion, and off the alu pipe.
+__device__ __forceinline__ void sbox7_limbs(uint64_t x, double& lo, double& hi) {
+    const uint64_t x2 = gl::sqr(x);
+    const uint64_t x4 = gl::sqr(x2);
+    const uint64_t x3 = gl::mul(x, x2);
+    uint32_t z0, z1, z2, z3;
+    gl::mul_words(x3, x4, z0, z1, z2, z3);
+    const double d2 = biased(z2);
+    lo = __dsub_rn(__dsub_rn(biased(z0), d2), __dsub_rn(biased(z3), TWO52));
+    hi = __dsub_rn(__dadd_rn(biased(z1), __dsub_rn(d2, TWO52)), TWO52);
+}
+
+// One limb of the MDS layer.  s[12]: exact integers (|s| < 2^41); k[12]: folded constants (uu0..2, uv0..2, v0..5);
 // o[r] = sum_i s[(i+r)%12]*CIRC[i] + (r==0)*8*s[0] + c[r], with c (and the 2^52 read-out bias) folded into k.
 // Mirrors tools/mds_model.py · mds_limb operation by operation.
 __device__ __forceinline__ void mds_limb(const double (&s)[WIDTH], const double* __restrict__ k, double (&o)[WIDTH]) {
@@ -90,7 +106,7 @@ __device__ __forceinline__ void mds_limb(const double (&s)[WIDTH], const double*
     }
 }
 
-// (2^52 + al, 2^52 + ah) -> the 64-bit "any" word congruent to al + ah*2^32 (al, ah < 2^52; here < 2^43).
+// (2^52 + al, 2^52 + ah) -> the 64-bit "any" word congruent to al + ah*2^32 (al, ah < 2^52; here < 2^50).
 // With a1 = al >> 32, b1 = ah >> 32:  al + ah*2^32 = a0 + (a1 + b1 + b0)*2^32 + b1*(2^64 - 2^32), and 2^64 = 2^32 - 1
 // turns the last term into -b1; the single possible carry k out of the middle word is folded the same way.  No
 // conditional fix-up is needed (tools/word_model.py · recombine_model).
@@ -111,16 +127,14 @@ __device__ __forceinline__ uint64_t recombine(double AL, double AH) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// s <- MDS * s + (constants of layer `layer`)   — "any" in, "any" out
-__device__ __forceinline__ void mds_layer(uint64_t (&s)[WIDTH], int layer) {
-    const double* __restrict__ k = POSEIDON_MDS_K[layer];
-    double in[WIDTH], AL[WIDTH], AH[WIDTH];
+// S-boxes on every lane, then s <- MDS * s + (constants of layer r): "any" in, "any" out
+__device__ __forceinline__ void full_round(uint64_t (&s)[WIDTH], int r) {
+    const double* __restrict__ k = POSEIDON_MDS_K[r];
+    double lo[WIDTH], hi[WIDTH], AL[WIDTH], AH[WIDTH];
 #pragma unroll
-    for (int i = 0; i < WIDTH; i++) in[i] = limb_to_double((uint32_t)s[i]);
-    mds_limb(in, k, AL);
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) in[i] = limb_to_double((uint32_t)(s[i] >> 32));
-    mds_limb(in, k + WIDTH, AH);
+    for (int i = 0; i < WIDTH; i++) sbox7_limbs(s[i], lo[i], hi[i]);
+    mds_limb(lo, k, AL);
+    mds_limb(hi, k + WIDTH, AH);
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = recombine(AL[i], AH[i]);
 }
@@ -191,12 +205,6 @@ __device__ __forceinline__ void normalize_limbs(double& L, double& H) {
     L = __dsub_rn(L, cH);
 }
 
-__device__ __forceinline__ void full_round(uint64_t (&s)[WIDTH], int r) {
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) s[i] = sbox7(s[i]);
-    mds_layer(s, r);
-}
-
 __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     double L[WIDTH], H[WIDTH];
 #pragma unroll
@@ -207,9 +215,7 @@ __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     uint64_t x0 = s[0];
 #pragma unroll 1
     for (int r = N_FULL_HALF; r < N_FULL_HALF + N_PARTIAL; r++) {
-        x0 = sbox7(x0);
-        L[0] = limb_to_double((uint32_t)x0);
-        H[0] = limb_to_double((uint32_t)(x0 >> 32));
+        sbox7_limbs(x0, L[0], H[0]);
         double OL[WIDTH], OH[WIDTH];
         mds_limb_partial(L, POSEIDON_PARTIAL_Q[r - N_FULL_HALF][0], OL);
         mds_limb_partial(H, POSEIDON_PARTIAL_Q[r - N_FULL_HALF][1], OH);

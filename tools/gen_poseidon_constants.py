@@ -60,17 +60,18 @@ def mds_tables(rc):
     """Folded fp64 constants of the MDS layer that follows round r (tools/mds_model.py): per layer 2 limbs x
     (uu0..2, uv0..2, v0..5).  The constant of lane i is RC[12(r+1)+i] (0 after the last round), split into two limbs
     that are multiples of 4 (4*limbs of rc/4 mod p) so that every folded value is an integer; 2^52 is added to every
-    lane so that the sums leave the fp64 pipe as 2^52 + integer, i.e. with the integer in the mantissa bits."""
+    lane so that the sums leave the fp64 pipe as 2^52 + integer, i.e. with the integer in the mantissa bits, plus the
+    positivity offsets OFF_LO / OFF_HI (OFF_LO + OFF_HI*2^32 = 2^17 p) because the S-box hands over a signed low limb."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from mds_model import fold_constants, rc_limbs
+    from mds_model import fold_constants, rc_limbs, OFF_LO, OFF_HI
     rows = []
     for r in range(30):
         lanes = [rc[12 * (r + 1) + i] if r < 29 else 0 for i in range(12)]
         limbs = [rc_limbs(c) for c in lanes]
         row = []
         for limb in (0, 1):
-            k = fold_constants([l[limb] + (1 << 52) for l in limbs])
+            k = fold_constants([l[limb] + (1 << 52) + (OFF_LO, OFF_HI)[limb] for l in limbs])
             assert all(x.denominator == 1 and abs(x) < (1 << 53) for x in k)
             row += [int(x) for x in k]
         rows.append(row)

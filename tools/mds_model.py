@@ -158,31 +158,43 @@ def sbox(x):
     return pow(x, 7, P)
 
 
+def sbox_limbs(x, rnd=None):
+    """x^7 as the two signed limbs the CUDA S-box hands to the fp64 MDS: the 128-bit product x^3 * x^4 = (z3:z2:z1:z0) is
+    not reduced to 64 bits; with 2^64 = 2^32 - 1 and 2^96 = -1 its value is (z0 - z2 - z3) + (z1 + z2)*2^32."""
+    x2 = x * x % P; x4 = x2 * x2 % P; x3 = x * x2 % P
+    z = x3 * x4
+    z0, z1, z2, z3 = (z >> 0) & 0xFFFFFFFF, (z >> 32) & 0xFFFFFFFF, (z >> 64) & 0xFFFFFFFF, z >> 96
+    lo, hi = z0 - z2 - z3, z1 + z2
+    assert (lo + (hi << 32)) % P == pow(x, 7, P)
+    return lo, hi
+
+
 def permute_v3(state, rc, stats=None):
     """Mirror of csrc/poseidon.cuh · permute (v3) on exact integers."""
     lane0_c, tail_c = partial_constants(rc)
     s = [(state[i] + rc[i]) % P for i in range(12)]
 
-    def full_layer(s, r):
+    def full_layer(lo, hi, r):
         lanes = [rc[12 * (r + 1) + i] if r < 29 else 0 for i in range(12)]
         limbs = [rc_limbs(c) for c in lanes]
         out = []
-        for limb in (0, 1):
-            k = [int(x) for x in fold_constants([l[limb] + BIAS for l in limbs])]
-            ins = [(v >> (32 * limb)) & 0xFFFFFFFF for v in s]
+        for limb, ins, off in ((0, lo, OFF_LO), (1, hi, OFF_HI)):
+            k = [int(x) for x in fold_constants([l[limb] + BIAS + off for l in limbs])]
             o = mds_limb_checked(ins, k)
             assert all(BIAS <= x < 2 * BIAS for x in o)
             out.append([x - BIAS for x in o])
         return [(out[0][i] + (out[1][i] << 32)) % P for i in range(12)]
 
+    def full_round(s, r):
+        lo, hi = zip(*[sbox_limbs(x) for x in s])
+        return full_layer(list(lo), list(hi), r)
+
     for r in range(0, 4):
-        s = [sbox(x) for x in s]
-        s = full_layer(s, r)
+        s = full_round(s, r)
     x0 = s[0]
     L = [v & 0xFFFFFFFF for v in s]; H = [v >> 32 for v in s]          # lanes 1..11 resident (index 0 unused)
     for r in range(4, 26):
-        x0 = sbox(x0)
-        L[0], H[0] = x0 & 0xFFFFFFFF, x0 >> 32
+        L[0], H[0] = sbox_limbs(x0)
         c0 = lane0_c[r + 1]
         cl, ch = rc_limbs(c0)
         outs = []
@@ -210,8 +222,7 @@ def permute_v3(state, rc, stats=None):
         assert BIAS <= al < 2 * BIAS and BIAS <= ah < 2 * BIAS
         s.append(((al - BIAS) + ((ah - BIAS) << 32)) % P)
     for r in range(26, 30):
-        s = [sbox(x) for x in s]
-        s = full_layer(s, r)
+        s = full_round(s, r)
     return s
 
 
