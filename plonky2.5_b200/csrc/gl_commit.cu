@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <utility>
@@ -160,6 +161,9 @@ struct gl_ctx {
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
     std::map<gl_handle, std::unique_ptr<Fri>> fris;
     gl_handle next_handle = 1;
+    cudaStream_t copy_stream = nullptr;   // host->device column copies of gl_commit, overlapped with the NTTs
+    cudaEvent_t ev_sync = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t ev[GL_N_STAGES + 1] = {};
     float stage_ms[GL_N_STAGES] = {};
     uint32_t launches[GL_N_STAGES] = {};
@@ -326,38 +330,48 @@ Fri* find_fri(gl_ctx* c, gl_handle h) {
 
 void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream)); }
 
-// iNTT + coset LDE of a device column-major matrix into row-major outputs (shared by gl_commit / gl_dev_*)
-void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
-               int is_coeffs, uint64_t* d_coeffs, uint32_t coeff_pitch, uint64_t* d_rows, uint32_t row_pitch, bool timed) {
+// iNTT + coset LDE of `n_cols` device columns (column-major, col_stride apart) into columns [col0, col0 + padded) of the
+// row-major outputs.  Column groups are independent, so a batch can be processed in chunks (pipelined behind the
+// host->device copies in gl_commit).  col0 must be a multiple of 8.
+void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t col0, uint32_t n_cols, uint32_t width,
+                 uint32_t log_n, uint32_t rate_bits, int is_coeffs, uint64_t* d_vals, uint64_t* d_coeffs, uint32_t coeff_pitch,
+                 uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events) {
     const uint64_t N = 1ULL << log_n;
-    // column groups of 8 words (64 B row segments); a narrow shard whose padding to 8 would waste >= 4 columns runs
-    // in groups of 4 (32 B = one sector) instead
-    const int G = (round_up(n_cols, 8) - n_cols >= 4 && coeff_pitch % 4 == 0 && row_pitch % 4 == 0) ? 4 : 8;
     const uint32_t cols_padded = round_up(n_cols, G);
     dim3 tb(32, 8);
-    dim3 tg((uint32_t)((N + 31) / 32), (coeff_pitch + 31) / 32);
+    dim3 tg((uint32_t)((N + 31) / 32), (width + 31) / 32);
     uint32_t* l_tr = timed ? &c->launches[GL_STAGE_TRANSPOSE] : nullptr;
     uint32_t* l_in = timed ? &c->launches[GL_STAGE_INTT] : nullptr;
     uint32_t* l_ld = timed ? &c->launches[GL_STAGE_LDE] : nullptr;
+    uint64_t* coeffs = d_coeffs + col0;
     if (is_coeffs) {
-        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, d_coeffs, coeff_pitch, n_cols, N);
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, coeffs, coeff_pitch, width, n_cols, N);
         CUDA_CHECK(cudaGetLastError());
         if (l_tr) (*l_tr)++;
-        if (timed) { record(c, GL_STAGE_INTT); }
+        if (split_events) record(c, GL_STAGE_INTT);
     } else {
-        c->vals.ensure(N * coeff_pitch);
-        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, c->vals.p, coeff_pitch, n_cols, N);
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, d_vals + col0, coeff_pitch, width, n_cols, N);
         CUDA_CHECK(cudaGetLastError());
         if (l_tr) (*l_tr)++;
-        if (timed) record(c, GL_STAGE_INTT);
-        run_ntt(c, c->vals.p, coeff_pitch, d_coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, G, l_in);
+        if (split_events) record(c, GL_STAGE_INTT);
+        run_ntt(c, d_vals + col0, coeff_pitch, coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, G, l_in);
     }
-    if (timed) record(c, GL_STAGE_LDE);
+    if (split_events) record(c, GL_STAGE_LDE);
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
     for (uint32_t s = 0; s < (1u << rate_bits); s++) {
-        uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch;
-        run_ntt(c, d_coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
+        uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch + col0;
+        run_ntt(c, coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
     }
+}
+
+void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+               int is_coeffs, uint64_t* d_coeffs, uint32_t coeff_pitch, uint64_t* d_rows, uint32_t row_pitch, bool timed) {
+    // column groups of 8 words (64 B row segments); a narrow shard whose padding to 8 would waste >= 4 columns runs
+    // in groups of 4 (32 B = one sector) instead
+    const int G = (round_up(n_cols, 8) - n_cols >= 4 && coeff_pitch % 4 == 0 && row_pitch % 4 == 0) ? 4 : 8;
+    if (!is_coeffs) c->vals.ensure(((uint64_t)1 << log_n) * coeff_pitch);
+    lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, is_coeffs, c->vals.p, d_coeffs, coeff_pitch, d_rows,
+                row_pitch, G, timed, timed);
 }
 
 int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_cols_in, uint64_t col_stride, uint32_t n_cols,
@@ -382,18 +396,41 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
     memset(c->launches, 0, sizeof c->launches);
 
     record(c, GL_STAGE_H2D);
-    const uint64_t* d_cols = d_cols_in;
     if (host_cols) {
-        c->in_stage.ensure(N * n_cols);
-        for (uint32_t j = 0; j < n_cols; j++) {
+        // Host columns: copy in chunks of CHUNK columns on the copy stream and run transpose + iNTT + LDE of chunk k on the
+        // compute stream while chunk k+1 is still crossing PCIe (column groups are independent polynomials).  With pinned
+        // host memory the copies overlap completely; the stage split then reads h2d = first chunk, lde = everything else.
+        constexpr uint32_t CHUNK = 24;
+        for (uint32_t j = 0; j < n_cols; j++)
             if (!host_cols[j]) GL_THROW(GL_ERR_INVALID, "cols[%u] is NULL", j);
-            CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, host_cols[j], N * 8, cudaMemcpyHostToDevice, c->stream));
+        c->in_stage.ensure(N * n_cols);
+        if (!is_coeffs) c->vals.ensure(N * pitch);
+        const uint32_t n_chunks = (n_cols + CHUNK - 1) / CHUNK;
+        if (c->chunk_ev.size() < n_chunks) {
+            size_t old = c->chunk_ev.size();
+            c->chunk_ev.resize(n_chunks, nullptr);
+            for (size_t i = old; i < n_chunks; i++) CUDA_CHECK(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
         }
-        d_cols = c->in_stage.p;
-        col_stride = N;
+        CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));              // in_stage may still be read by an earlier call
+        CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
+        for (uint32_t k = 0; k < n_chunks; k++) {
+            const uint32_t c0 = k * CHUNK, nc = std::min(CHUNK, n_cols - c0);
+            for (uint32_t j = c0; j < c0 + nc; j++)
+                CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, host_cols[j], N * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            CUDA_CHECK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
+        }
+        for (uint32_t k = 0; k < n_chunks; k++) {
+            const uint32_t c0 = k * CHUNK, nc = std::min(CHUNK, n_cols - c0);
+            const uint32_t width = std::min(round_up(nc, 8), pitch - c0);
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[k], 0));
+            if (k == 0) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); }
+            lde_columns(c, c->in_stage.p + (uint64_t)c0 * N, N, c0, nc, width, log_n, rate_bits, is_coeffs, c->vals.p, t->coeffs.p, pitch,
+                        t->leaves.p, pitch, 8, true, false);
+        }
+    } else {
+        record(c, GL_STAGE_TRANSPOSE);
+        lde_stage(c, d_cols_in, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
     }
-    record(c, GL_STAGE_TRANSPOSE);
-    lde_stage(c, d_cols, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
     record(c, GL_STAGE_LEAF_HASH);
     merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
                  &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
@@ -434,6 +471,7 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
     catch (const GlError& e) {                   \
         (ctx)->err = e.msg;                      \
         cudaGetLastError();                      \
+        if ((ctx)->copy_stream) cudaStreamSynchronize((ctx)->copy_stream); /* host buffers are only borrowed */ \
         return e.code;                           \
     }                                            \
     catch (const std::bad_alloc&) {              \
@@ -472,6 +510,8 @@ int gl_ctx_create(gl_ctx** out, int device) {
     if (!c) return GL_ERR_OOM;
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -490,6 +530,9 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->in_stage.release(); c->vals.release(); c->scratch.release();
     DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -169,7 +169,8 @@ __global__ void ntt_tiny_kernel(const uint64_t* __restrict__ src, uint64_t* __re
 // Column-major [n_cols][n_rows] (contiguous columns, as plonky2's Vec<PolynomialValues>) -> row-major
 // [n_rows][pitch], canonicalising on the way.  32x32 tiles through shared memory.
 __global__ void transpose_in_kernel(const uint64_t* __restrict__ src, uint64_t src_col_stride, uint64_t* __restrict__ dst,
-                                    uint32_t pitch, uint32_t n_cols, uint64_t n_rows) {
+                                    uint32_t pitch, uint32_t width, uint32_t n_cols, uint64_t n_rows) {
+    // writes columns [0, width) of dst (row stride `pitch`): the n_cols source columns, zero beyond them
     __shared__ uint64_t t[32][33];
     uint64_t r0 = (uint64_t)blockIdx.x * 32;
     uint32_t c0 = blockIdx.y * 32;
@@ -182,7 +183,7 @@ __global__ void transpose_in_kernel(const uint64_t* __restrict__ src, uint64_t s
     for (uint32_t i = threadIdx.y; i < 32; i += blockDim.y) {
         uint64_t r = r0 + i;
         uint32_t c = c0 + threadIdx.x;
-        if (r < n_rows && c < pitch) dst[r * pitch + c] = t[threadIdx.x][i];
+        if (r < n_rows && c < width) dst[r * pitch + c] = t[threadIdx.x][i];
     }
 }
 
