@@ -143,6 +143,14 @@ int gl_ctx_stage_times(gl_ctx* ctx, float* out_ms, uint32_t* out_launches);
  * 3: Goldilocks modmul, 4: Poseidon permutation} on every SM, returns operations per second in *out_ops_per_s */
 int gl_microbench(gl_ctx* ctx, int which, uint32_t iters, double* out_ops_per_s);
 
+/* element-wise field primitives exactly as the kernels use them (carry-logic unit tests on adversarial words).
+ * out[i] = op(a[i], b[i]) canonicalised, or the raw 64-bit representative when GL_FOP_RAW is or-ed in.             */
+enum {
+    GL_FOP_MUL = 0, GL_FOP_ADD_ANY = 1, GL_FOP_SUB_ANY = 2, GL_FOP_MUL_2_24 = 3, GL_FOP_MUL_2_48 = 4, GL_FOP_MUL_2_72 = 5,
+    GL_FOP_SBOX7 = 6, GL_FOP_ADD_ANY_C = 7, GL_FOP_RAW = 0x100
+};
+int gl_field_op(gl_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n);
+
 /* pinned host memory for benchmarks / shims that want fast PCIe copies */
 void* gl_host_alloc(size_t bytes);
 void gl_host_free(void* p);

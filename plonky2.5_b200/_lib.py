@@ -53,6 +53,7 @@ SIGNATURES = {
     "gl_dev_merkle": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]),
     "gl_ctx_stage_times": (c_int, [c_void_p, POINTER(c_float), POINTER(c_uint32)]),
     "gl_microbench": (c_int, [c_void_p, c_int, c_uint32, POINTER(c_double)]),
+    "gl_field_op": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint64]),
     "gl_host_alloc": (c_void_p, [c_size_t]),
     "gl_host_free": (None, [c_void_p]),
 }

@@ -86,6 +86,14 @@ class Context:
         _check(self, self.lib.gl_microbench(self.handle, which, iters, byref(out)))
         return out.value
 
+    def field_op(self, op: int, a: np.ndarray, b: Optional[np.ndarray] = None) -> np.ndarray:
+        """Element-wise field primitive exactly as the kernels use it (include/gl_commit.h · GL_FOP_*)."""
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+        b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1)
+        out = np.zeros_like(a)
+        _check(self, self.lib.gl_field_op(self.handle, op, _ptr(a), _ptr(b), _ptr(out), a.size))
+        return out
+
     def poseidon_permute(self, states: np.ndarray) -> np.ndarray:
         s = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, SPONGE_WIDTH).copy()
         _check(self, self.lib.gl_poseidon_permute(self.handle, _ptr(s), s.shape[0]))

@@ -226,7 +226,7 @@ void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* l
     p.ncg = cols_padded / G;
     uint32_t T = 1u << p.a;
     uint32_t threads = T * G / 8;
-    size_t smem = ((size_t)(T + (T >> 3)) * G + (T >> 1)) * 8;
+    size_t smem = ((size_t)(T + (T >> 3)) * G + (T - (T >> 3))) * 8;   // padded tile + 7T/8 twiddles
     uint64_t grid = (uint64_t)p.ncg << (p.log_n - p.a);
     if (grid >= (1ULL << 31)) GL_THROW(GL_ERR_UNSUPPORTED, "NTT grid too large");
     ntt::ntt_pass_kernel<G><<<(uint32_t)grid, threads, smem, c->stream>>>(p);
@@ -861,6 +861,48 @@ int gl_poseidon_permute(gl_ctx* c, uint64_t* states, uint64_t n) {
     merkle::permute_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, c->stream>>>(c->scratch.p, n);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(states, c->scratch.p, 96 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+// element-wise field primitives exactly as the kernels use them (unit tests of the carry logic on adversarial words)
+__global__ void field_op_kernel(int op, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t* __restrict__ out,
+                                uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = a[i], y = b[i], r = 0;
+    switch (op & ~GL_FOP_RAW) {
+        case GL_FOP_MUL: r = gl::mul(x, y); break;
+        case GL_FOP_ADD_ANY: r = gl::add_any(x, y); break;
+        case GL_FOP_SUB_ANY: r = gl::sub_any(x, y); break;
+        case GL_FOP_MUL_2_24: r = gl::mul_2_24(x); break;
+        case GL_FOP_MUL_2_48: r = gl::mul_2_48(x); break;
+        case GL_FOP_MUL_2_72: r = gl::mul_2_72(x); break;
+        case GL_FOP_SBOX7: {
+            double lo, hi;
+            poseidon::sbox7_limbs(x, lo, hi);
+            // same read-out as the MDS layer: bias + positivity offset, then recombine (offsets are = 0 mod p)
+            r = poseidon::recombine(__dadd_rn(lo, 4503599627370496.0 + 562949953552384.0), __dadd_rn(hi, 4503599627370496.0 + 562949953159168.0));
+            break;
+        }
+        case GL_FOP_ADD_ANY_C: r = gl::add_any_c(x, gl::canon(y)); break;
+        default: break;
+    }
+    out[i] = (op & GL_FOP_RAW) ? r : gl::canon(r);
+}
+
+int gl_field_op(gl_ctx* c, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    GL_API_BEGIN(c)
+    if (!a || !b || !out) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if ((op & ~GL_FOP_RAW) < 0 || (op & ~GL_FOP_RAW) > GL_FOP_ADD_ANY_C) GL_THROW(GL_ERR_INVALID, "unknown field op %d", op);
+    if (n == 0) return GL_OK;
+    c->scratch.ensure(3 * n);
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p, a, 8 * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p + n, b, 8 * n, cudaMemcpyHostToDevice, c->stream));
+    field_op_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, c->stream>>>(op, c->scratch.p, c->scratch.p + n, c->scratch.p + 2 * n, n);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, c->scratch.p + 2 * n, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return GL_OK;
     GL_API_END(c)

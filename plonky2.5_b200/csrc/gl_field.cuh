@@ -95,6 +95,52 @@ __device__ __forceinline__ uint64_t add_any_c(uint64_t a, uint64_t b) {
     return s;
 }
 
+// any + any -> any.  A 64-bit carry is worth 2^64 = 2^32 - 1; folding it can carry once more (only when the wrapped sum
+// is >= p), never a third time.
+__device__ __forceinline__ uint64_t add_any(uint64_t a, uint64_t b) {
+    uint32_t l, h;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "add.cc.u32  %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32    m, 0, 0;\n\t"     // (subc after add.cc is NOT the carry: sm_100 keeps borrows as inverted carries)
+        "neg.s32     m, m;\n\t"        // 0xFFFFFFFF * carry = (2^32 - 1) * carry
+        "add.cc.u32  %0, %0, m;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.u32    m, 0, 0;\n\t"
+        "neg.s32     m, m;\n\t"
+        "add.cc.u32  %0, %0, m;\n\t"
+        "addc.u32    %1, %1, 0;\n\t"
+        "}" : "=&r"(l), "=&r"(h) : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+    return ((uint64_t)h << 32) | l;
+}
+// any - any -> any (a borrow is worth -(2^32 - 1); the fold can borrow once more, never a third time)
+__device__ __forceinline__ uint64_t sub_any(uint64_t a, uint64_t b) {
+    uint32_t l, h;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32  %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32    m, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, m;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32    m, 0, 0;\n\t"
+        "sub.cc.u32  %0, %0, m;\n\t"
+        "subc.u32    %1, %1, 0;\n\t"
+        "}" : "=&r"(l), "=&r"(h) : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+    return ((uint64_t)h << 32) | l;
+}
+// x * 2^24 and x * 2^48 (any -> any): the 8th and 4th roots of unity of plonky2's root choice are powers of two
+// (w_8 = 2^120 = -2^24, w_4 = 2^48, w_8^3 = 2^168 = -2^72), so the radix-8 butterflies need shifts, not multiplies.
+__device__ __forceinline__ uint64_t mul_2_24(uint64_t x) {
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    return reduce_words(x0 << 24, __funnelshift_l(x0, x1, 24), x1 >> 8, 0u);
+}
+__device__ __forceinline__ uint64_t mul_2_48(uint64_t x) {
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    return reduce_words(0u, x0 << 16, __funnelshift_l(x0, x1, 16), x1 >> 16);
+}
+// 2^72 = (2^32 - 1) * 2^8 (mod p)
+__device__ __forceinline__ uint64_t mul_2_72(uint64_t x) { return mul(x, 0xFFFFFFFF00ULL); }
+
 __host__ __device__ __forceinline__ uint32_t bitrev32(uint32_t x, uint32_t bits) {
 #ifdef __CUDA_ARCH__
     return bits ? (__brev(x) >> (32 - bits)) : 0;

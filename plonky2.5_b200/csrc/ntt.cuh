@@ -12,8 +12,9 @@
 // out[i] = b[(n-i) mod n] is just the store address of the last pass.
 //
 // One pass = a 2^a-point DIF NTT (a <= 10) on index bits [log_blk-a, log_blk) of every block of 2^log_blk rows,
-// staged through shared memory in radix-8 register rounds, followed (if lower bits remain) by the inter-pass
-// twiddle w_{2^log_blk}^(o_lo * bitrev_a(l)) (four-step factorisation).  Stage twiddles come from a 2^(a-1)-entry
+// staged through shared memory in radix-8 register rounds (8-point DFTs whose roots are powers of two, i.e. shifts,
+// then one table twiddle per element), followed (if lower bits remain) by the inter-pass twiddle
+// w_{2^log_blk}^(o_lo * bitrev_a(l)) (four-step factorisation).  Round twiddles come from a 7*2^a/8-entry
 // shared-memory table; all roots come from one table W[e] = w_N^e (e < N/2) held by the context.
 #pragma once
 #include "gl_field.cuh"
@@ -40,35 +41,58 @@ __device__ __forceinline__ uint32_t ins3(uint32_t q, uint32_t sh, uint32_t e) {
 }
 __device__ __forceinline__ uint32_t phys_row(uint32_t l) { return l + (l >> 3); }   // bank-conflict padding
 
-__device__ __forceinline__ void bfly(uint64_t& u, uint64_t& v, uint64_t tw) {
-    uint64_t s = gl::add(u, v);
-    uint64_t d = gl::sub(u, v);
+__device__ __forceinline__ void addsub(uint64_t& u, uint64_t& v) {
+    const uint64_t s = gl::add_any(u, v);
+    v = gl::sub_any(u, v);
     u = s;
-    v = gl::mulc(d, tw);
 }
 
-// stages on thread-local bits k = nst-1 .. 0 of the 8 register elements; tile bit of local bit k is sh + k
+// In-place 8-point DIF with plonky2's power-of-two roots (w_8 = 2^120 = -2^24, w_4 = 2^48, w_8^3 = -2^72):
+// on return x[e] = sum_j x_j w_8^(j * bitrev3(e)).  "any" in, "any" out; 24 add/sub + 5 shift-multiplies, no table.
+__device__ __forceinline__ void dft8(uint64_t (&x)[8]) {
+    uint64_t s;
+    addsub(x[0], x[4]);
+    s = gl::add_any(x[1], x[5]); x[5] = gl::mul_2_24(gl::sub_any(x[5], x[1])); x[1] = s;   // * w_8   = -2^24
+    s = gl::add_any(x[2], x[6]); x[6] = gl::mul_2_48(gl::sub_any(x[2], x[6])); x[2] = s;   // * w_8^2 =  2^48
+    s = gl::add_any(x[3], x[7]); x[7] = gl::mul_2_72(gl::sub_any(x[7], x[3])); x[3] = s;   // * w_8^3 = -2^72
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        addsub(x[h], x[h + 2]);
+        s = gl::add_any(x[h + 1], x[h + 3]); x[h + 3] = gl::mul_2_48(gl::sub_any(x[h + 1], x[h + 3])); x[h + 1] = s;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) addsub(x[e], x[e + 1]);
+}
+
+// One register round on the 8 elements of a thread: `nst` DIF stages on thread-local bits nst-1..0 (tile bit of local
+// bit k is sh + k).  nst == 3 is a radix-8 step of a block of m = 2^(sh+3) tile rows: 8-point DFT, then element e is
+// multiplied by w_m^(i * bitrev3(e)), i = position inside the sub-block (Wl[j] = w_T^j, j < 7T/8).  nst < 3 only
+// happens with sh == 0, where every twiddle is a power of w_4.
 __device__ __forceinline__ void radix8_round(uint64_t (&x)[8], const uint64_t* __restrict__ Wl, uint32_t a,
                                              uint32_t sh, uint32_t qlo, uint32_t nst) {
-    if (nst >= 3) {
-        const uint32_t shift = a - (sh + 2) - 1;
+    if (nst == 3) {
+        dft8(x);
+        if (sh != 0) {
+            const uint32_t step = qlo << (a - sh - 3);
 #pragma unroll
-        for (int e = 0; e < 4; e++) bfly(x[e], x[e + 4], Wl[(((uint32_t)e << sh) | qlo) << shift]);
-    }
-    if (nst >= 2) {
-        const uint32_t shift = a - (sh + 1) - 1;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            uint64_t tw = Wl[(((uint32_t)e << sh) | qlo) << shift];
-            bfly(x[e], x[e + 2], tw);
-            bfly(x[e + 4], x[e + 6], tw);
+            for (int e = 1; e < 8; e++) {
+                const uint32_t k = ((e & 1) << 2) | (e & 2) | (e >> 2);
+                x[e] = gl::mul(x[e], Wl[step * k]);
+            }
         }
-    }
-    {
-        const uint32_t shift = a - sh - 1;
-        uint64_t tw = Wl[qlo << shift];
+    } else if (nst == 2) {
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) bfly(x[e], x[e + 1], tw);
+        for (int h = 0; h < 8; h += 4) {
+            addsub(x[h], x[h + 2]);
+            const uint64_t s = gl::add_any(x[h + 1], x[h + 3]);
+            x[h + 3] = gl::mul_2_48(gl::sub_any(x[h + 1], x[h + 3]));
+            x[h + 1] = s;
+            addsub(x[h], x[h + 1]);
+            addsub(x[h + 2], x[h + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) addsub(x[e], x[e + 1]);
     }
 }
 
@@ -86,7 +110,9 @@ __global__ void ntt_pass_kernel(const PassParams p) {
     const uint32_t row_base = (o_hi << p.log_blk) | o_lo;
     const uint32_t col = cg * G + c;
 
-    for (uint32_t e = tid; e < (T >> 1); e += nthr) Wl[e] = p.W[(size_t)e << (p.log_n - a)];
+    // Wl[e] = w_T^e for e < 7T/8 (radix-8 twiddle exponents reach 7 * (T/8 - 1)); the upper part is -w_T^(e - T/2)
+    for (uint32_t e = tid; e < T - (T >> 3); e += nthr)
+        Wl[e] = e < (T >> 1) ? p.W[(size_t)e << (p.log_n - a)] : gl::P - p.W[(size_t)(e - (T >> 1)) << (p.log_n - a)];
 
     uint64_t x[8];
     uint32_t sh = a - 3;
@@ -102,7 +128,7 @@ __global__ void ntt_pass_kernel(const PassParams p) {
             if (pre) {
                 uint64_t f = p.preA[l];
                 if (b_lo) f = gl::mul(f, bv);
-                v = gl::mulc(v, f);
+                v = gl::mul(v, f);
             }
             x[e] = v;
         }
@@ -134,9 +160,10 @@ __global__ void ntt_pass_kernel(const PassParams p) {
             uint64_t w;
             if (ex >= (N >> 1)) w = gl::P - p.W[ex - (N >> 1)];
             else w = p.W[ex];
-            v = gl::mulc(v, w);
+            v = gl::mul(v, w);
         }
-        if (p.scale != 1) v = gl::mulc(v, p.scale);
+        if (p.scale != 1) v = gl::mul(v, p.scale);
+        v = gl::canon(v);
         uint32_t prow = row_base | (l << b_lo);
         uint32_t drow = p.store_mode == 1 ? ((N - gl::bitrev32(prow, p.log_n)) & (N - 1)) : prow;
         p.dst[(uint64_t)drow * p.dst_pitch + col] = v;

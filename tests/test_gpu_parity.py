@@ -225,3 +225,35 @@ def test_stage_times_and_launch_counts(ctx):
     ms, launches = ctx.stage_times()
     assert launches["leaf_hash"] == 1 and launches["tree"] == 13 - 4 and launches["lde"] == 8 and launches["intt"] == 1
     assert all(v >= 0 for v in ms.values())
+
+
+def _edge_words():
+    e = [0, 1, 2, 0xFFFFFFFE, 0xFFFFFFFF, 1 << 32, (1 << 32) + 1, P - 2, P - 1, P, P + 1, 2**64 - 2, 2**64 - 1, 0xFFFFFFFF << 32,
+         (0xFFFFFFFF << 32) | 1, 1 << 63, (1 << 63) - 1, 0xFFFFFFFE00000001, 0xFFFFFFFE00000002, 0x00000001FFFFFFFF, 0xFFFFFF, 1 << 40]
+    return e
+
+
+def test_field_primitives_on_adversarial_words(ctx):
+    """gl::mul / add_any / sub_any / shift multiplies / S-box exactly as the kernels use them, on every pair of edge words
+    (carry and double-carry corners that random data reaches with probability 2^-32) and on random words."""
+    from plonky25_b200 import _lib  # noqa: F401
+    rng = np.random.default_rng(11)
+    e = _edge_words()
+    a = np.array([x for x in e for _ in e] + rng.integers(0, 2**64, 20000, dtype=np.uint64).tolist(), dtype=np.uint64)
+    b = np.array([y for _ in e for y in e] + rng.integers(0, 2**64, 20000, dtype=np.uint64).tolist(), dtype=np.uint64)
+    ai, bi = [int(x) for x in a], [int(y) for y in b]
+    FOP = dict(mul=0, add_any=1, sub_any=2, mul_2_24=3, mul_2_48=4, mul_2_72=5, sbox7=6, add_any_c=7)
+    want = {
+        "mul": [x * y % P for x, y in zip(ai, bi)],
+        "add_any": [(x + y) % P for x, y in zip(ai, bi)],
+        "sub_any": [(x - y) % P for x, y in zip(ai, bi)],
+        "mul_2_24": [(x << 24) % P for x in ai],
+        "mul_2_48": [(x << 48) % P for x in ai],
+        "mul_2_72": [(x << 72) % P for x in ai],
+        "sbox7": [pow(x, 7, P) for x in ai],
+        "add_any_c": [(x + y) % P for x, y in zip(ai, bi)],
+    }
+    for name, op in FOP.items():
+        got = ctx.field_op(op, a, b).tolist()
+        bad = [i for i, (g_, w_) in enumerate(zip(got, want[name])) if g_ != w_]
+        assert not bad, f"{name}: {len(bad)} mismatches, first a={ai[bad[0]]:#x} b={bi[bad[0]]:#x} got={got[bad[0]]:#x} want={want[name][bad[0]]:#x}"

@@ -55,6 +55,34 @@ def reduce_model(z0, z1, z2, z3):
     return l | h << 32
 
 
+def add_any_model(a, b):
+    f = Flags()
+    l = add_cc(f, a & M32, b & M32); h = addc_cc(f, a >> 32, b >> 32); m = (-addc(f, 0, 0)) & M32
+    l = add_cc(f, l, m); h = addc_cc(f, h, 0); m = (-addc(f, 0, 0)) & M32
+    l = add_cc(f, l, m); h = addc_cc(f, h, 0)
+    assert f.cf == 0
+    return l | h << 32
+
+
+def sub_any_model(a, b):
+    f = Flags()
+    l = sub_cc(f, a & M32, b & M32); h = subc_cc(f, a >> 32, b >> 32); m = subc(f, 0, 0)
+    l = sub_cc(f, l, m); h = subc_cc(f, h, 0); m = subc(f, 0, 0)
+    l = sub_cc(f, l, m); h = subc_cc(f, h, 0)
+    assert f.cf == 0
+    return l | h << 32
+
+
+def mul_2_24_model(x):
+    x0, x1 = x & M32, x >> 32
+    return reduce_model((x0 << 24) & M32, ((x1 << 24) | (x0 >> 8)) & M32, x1 >> 8, 0)
+
+
+def mul_2_48_model(x):
+    x0, x1 = x & M32, x >> 32
+    return reduce_model(0, (x0 << 16) & M32, ((x1 << 16) | (x0 >> 16)) & M32, x1 >> 16)
+
+
 def recombine_model(al, ah):
     """value = al + ah*B (al, ah < 2^52 as they sit in the mantissa of 2^52 + x) -> 64-bit 'any'."""
     a0, a1, b0, b1 = al & M32, al >> 32, ah & M32, ah >> 32
@@ -84,4 +112,12 @@ if __name__ == "__main__":
         ah = rnd.choice([0, 1, M32, B, (1 << 52) - 1, rnd.getrandbits(52), rnd.getrandbits(42), rnd.getrandbits(33)])
         r = recombine_model(al, ah)
         assert r < (1 << 64) and r % P == (al + (ah << 32)) % P, (hex(al), hex(ah))
+    for a, b in cases:
+        for fn, want in ((add_any_model, a + b), (sub_any_model, a - b)):
+            r = fn(a, b)
+            assert 0 <= r < (1 << 64) and r % P == want % P, (fn.__name__, hex(a), hex(b), hex(r))
+        for fn, sh in ((mul_2_24_model, 24), (mul_2_48_model, 48)):
+            r = fn(a)
+            assert 0 <= r < (1 << 64) and r % P == (a << sh) % P, (fn.__name__, hex(a))
+    assert (0xFFFFFFFF00 - pow(2, 72, P)) % P == 0
     print("word model ok")
