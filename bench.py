@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=17, help="rows (log2) of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU column->row exchange (DESIGN.md §6)")
     return ap.parse_args()
 
 
@@ -213,7 +214,7 @@ def main():
         plan = sharded.ShardPlan(cols, log_n, r, h, world)
         c0, c1 = plan.col_range(rank)
         d_cols = synth_columns(torch, dev, cols, n, 1)[c0:c1].contiguous()
-        state = sharded.ShardedCommit(ctx, plan, rank, dist, torch)
+        state = sharded.ShardedCommit(ctx, plan, rank, dist, torch, exchange=a.exchange)
         torch.cuda.synchronize()
 
         def step():
@@ -306,6 +307,8 @@ def main():
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
                       if world == 1 else "pinned host shard -> device, sharded commit, cap to host"}
 
+    if world > 1:
+        state.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -352,7 +355,9 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
             "config": {"workload": workload_name(a), "log_n": log_n, "n_cols": cols, "rate_bits": r, "cap_height": h,
-                       "sharding": "none" if world == 1 else f"columns/{world} -> all-to-all -> leaf ranges/{world}",
+                       "sharding": "none" if world == 1 else (f"columns/{world} -> " + ("NTT stores into peer leaf buffers over NVLink (fused)"
+                                                                                  if a.exchange == "p2p" else "NCCL all-to-all + repack")
+                                                             + f" -> leaf ranges/{world}"),
                        "l2": "inputs (%.2f GB) and leaves (%.2f GB) exceed the 126 MB L2; no flush needed" % (cols * n * 8 / 1e9, R * cols * 8 / 1e9),
                        "permutations_per_step": perms_per_commit(log_n, cols, r, h)},
             "stage_ms": {k: round(v / a.steps, 4) for k, v in stage_acc.items()},

@@ -122,6 +122,19 @@ int gl_dev_commit(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint
 int gl_dev_lde(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
                uint32_t rate_bits, int input_is_coeffs, uint64_t* d_out_rows, uint32_t out_pitch,
                uint64_t* d_out_coeffs);
+/* stage 1 fused with the column->row exchange (one process per GPU, NVLink peer memory): like gl_dev_lde, but the last
+ * NTT pass of every coset stores each leaf-row segment directly into the leaf buffer of the rank that owns that row:
+ * global leaf row i lives in peer_leaves[i / (R/n_peers)] at row i % (R/n_peers), columns [col_off, col_off+n_cols) of
+ * a [R/n_peers][leaf_pitch] matrix.  peer_leaves: HOST array of n_peers device pointers (own buffer + buffers mapped
+ * with gl_dev_ipc_open).  The caller synchronises the ranks (barrier) before hashing.                                */
+int gl_dev_lde_scatter(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
+                       uint32_t rate_bits, int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers,
+                       uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch);
+/* CUDA IPC plumbing for the above: export a device buffer (64-byte handle) / map a peer's / unmap / free */
+int gl_dev_ipc_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]);
+int gl_dev_ipc_open(gl_ctx* ctx, const uint8_t handle[64], uint64_t** out_ptr);
+int gl_dev_ipc_close(gl_ctx* ctx, uint64_t* ptr);
+int gl_dev_ipc_free(gl_ctx* ctx, uint64_t* ptr);
 /* copy the first src_cols columns of a received [n_rows][src_pitch] block into columns
  * [dst_col_off, dst_col_off+src_cols) of [n_rows][dst_pitch] (canonicalising) */
 int gl_dev_repack(gl_ctx* ctx, const uint64_t* d_src, uint32_t src_pitch, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,

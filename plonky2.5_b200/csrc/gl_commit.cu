@@ -239,15 +239,18 @@ void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* l
 //                         later passes run in place on dst.
 //   ifft:                 all passes but the last run IN PLACE ON src (destroyed); last pass stores to dst in natural
 //                         coefficient order scaled by 1/N.
+//   scatter != nullptr (forward only): the last pass stores to the leaf owners (store_mode 2); dst is then only the
+//                         scratch the earlier passes work in.
 void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32_t dst_pitch, uint32_t cols_padded,
-             uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches) {
+             uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches, const ntt::Scatter* scatter = nullptr) {
     const uint64_t* W = get_roots(c, log_n);
     uint64_t n_inv = ifft ? gl::h_inv(((uint64_t)1 << log_n) % gl::P) : 1;
     auto passes = plan_passes(log_n);
     if (passes.empty()) {
         dim3 grid((cols_padded + 63) / 64, 1u << log_n);
         ntt::ntt_tiny_kernel<<<grid, 64, 0, c->stream>>>(src, dst, src_pitch, dst_pitch, cols_padded, log_n,
-                                                         gl::h_root_of_unity(log_n), pre ? pre->g : 1, ifft ? 1 : 0, n_inv);
+                                                         gl::h_root_of_unity(log_n), pre ? pre->g : 1, scatter ? 2 : (ifft ? 1 : 0), n_inv,
+                                                         scatter ? *scatter : ntt::Scatter{});
         CUDA_CHECK(cudaGetLastError());
         if (launches) (*launches)++;
         return;
@@ -264,6 +267,12 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
         p.preB = (first && pre) ? pre->B.p : nullptr;
         p.store_mode = (ifft && last) ? 1 : 0;
         p.scale = (ifft && last) ? n_inv : 1;
+        if (scatter && last) {
+            p.store_mode = 2;
+            memcpy(p.peer, scatter->peer, sizeof p.peer);
+            p.scatter_row0 = scatter->row0; p.log_rows_per_peer = scatter->log_rows_per_peer;
+            p.scatter_col0 = scatter->col0; p.scatter_pitch = scatter->pitch; p.scatter_ncols = scatter->ncols;
+        }
         if (ifft) {
             p.src = src; p.src_pitch = src_pitch;
             p.dst = last ? dst : src; p.dst_pitch = last ? dst_pitch : src_pitch;
@@ -335,7 +344,7 @@ void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream))
 // host->device copies in gl_commit).  col0 must be a multiple of 8.
 void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t col0, uint32_t n_cols, uint32_t width,
                  uint32_t log_n, uint32_t rate_bits, int is_coeffs, uint64_t* d_vals, uint64_t* d_coeffs, uint32_t coeff_pitch,
-                 uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events) {
+                 uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events, const ntt::Scatter* scatter = nullptr) {
     const uint64_t N = 1ULL << log_n;
     const uint32_t cols_padded = round_up(n_cols, G);
     dim3 tb(32, 8);
@@ -359,8 +368,14 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
     if (split_events) record(c, GL_STAGE_LDE);
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
     for (uint32_t s = 0; s < (1u << rate_bits); s++) {
-        uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch + col0;
-        run_ntt(c, coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
+        if (scatter) {   // d_rows is an [N][row_pitch] scratch reused by every coset (stream order)
+            ntt::Scatter sc = *scatter;
+            sc.row0 = (uint64_t)h_bitrev(s, rate_bits) * N;
+            run_ntt(c, coeffs, coeff_pitch, d_rows + col0, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld, &sc);
+        } else {
+            uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch + col0;
+            run_ntt(c, coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
+        }
     }
 }
 
@@ -576,6 +591,85 @@ int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
         CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                       int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
+                       uint64_t* d_out_coeffs, uint32_t coeff_pitch) {
+    GL_API_BEGIN(c)
+    check_shape(n_cols, log_n, rate_bits, 0);
+    if (!d_cols || !peer_leaves || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_peers == 0 || (n_peers & (n_peers - 1)) || n_peers > ntt::MAX_PEERS) GL_THROW(GL_ERR_INVALID, "n_peers must be a power of two <= %d", ntt::MAX_PEERS);
+    const uint64_t N = 1ULL << log_n, R = N << rate_bits;
+    if (R < n_peers) GL_THROW(GL_ERR_INVALID, "fewer leaf rows than peers");
+    if (coeff_pitch % 4 || coeff_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "coeff_pitch must be a multiple of 4 and >= n_cols");
+    const int G = (round_up(n_cols, 8) - n_cols >= 4) ? 4 : 8;
+    if (col_off + n_cols > leaf_pitch) GL_THROW(GL_ERR_INVALID, "columns do not fit the leaf pitch");
+    if (coeff_pitch < round_up(n_cols, G)) GL_THROW(GL_ERR_INVALID, "coeff_pitch too small for the padded column group");
+    ntt::Scatter sc{};
+    for (uint32_t q = 0; q < n_peers; q++) {
+        if (!peer_leaves[q]) GL_THROW(GL_ERR_INVALID, "peer_leaves[%u] is NULL", q);
+        sc.peer[q] = peer_leaves[q];
+    }
+    sc.log_rows_per_peer = log2_exact(R / n_peers);
+    sc.col0 = col_off;
+    sc.pitch = leaf_pitch;
+    sc.ncols = n_cols;
+    get_roots(c, log_n);
+    get_lde_tables(c, log_n, rate_bits);
+    c->scratch.ensure(N * coeff_pitch);      // pass scratch of one coset
+    if (!input_is_coeffs) c->vals.ensure(N * coeff_pitch);
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+    record(c, GL_STAGE_TRANSPOSE);
+    lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch,
+                c->scratch.p, coeff_pitch, G, true, true, &sc);
+    record(c, GL_STAGE_LEAF_HASH);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
+        CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+// ---- CUDA IPC: one process per GPU, each exports its leaf buffer and maps its peers' (NVLink peer access) -----------
+int gl_dev_ipc_alloc(gl_ctx* c, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]) {
+    GL_API_BEGIN(c)
+    if (!out_ptr || !out_handle || words == 0) GL_THROW(GL_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    uint64_t* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, words * 8));    // not pooled: an exported allocation must stay a whole cudaMalloc block
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); CUDA_CHECK(e); }
+    memcpy(out_handle, &h, 64);
+    *out_ptr = p;
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_ipc_open(gl_ctx* c, const uint8_t handle[64], uint64_t** out_ptr) {
+    GL_API_BEGIN(c)
+    if (!handle || !out_ptr) GL_THROW(GL_ERR_INVALID, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_ptr = (uint64_t*)p;
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_ipc_close(gl_ctx* c, uint64_t* ptr) {
+    GL_API_BEGIN(c)
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (ptr) CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_ipc_free(gl_ctx* c, uint64_t* ptr) {
+    GL_API_BEGIN(c)
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (ptr) CUDA_CHECK(cudaFree(ptr));
     return GL_OK;
     GL_API_END(c)
 }

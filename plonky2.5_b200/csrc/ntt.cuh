@@ -21,6 +21,8 @@
 
 namespace ntt {
 
+constexpr int MAX_PEERS = 16;
+
 struct PassParams {
     const uint64_t* src;
     uint64_t* dst;
@@ -32,8 +34,15 @@ struct PassParams {
     const uint64_t* W;               // w_N^e, e < max(N/2, 1), canonical
     const uint64_t* preA;            // coset pre-scale (first pass only) g^(l << (log_n-a)), l < 2^a, or nullptr
     const uint64_t* preB;            //                                   g^(o_lo), o_lo < 2^(log_n-a)
-    uint32_t store_mode;             // 0: row p -> p ; 1: iFFT: row p -> (N - bitrev_n(p)) mod N
+    uint32_t store_mode;             // 0: row p -> p ; 1: iFFT: row p -> (N - bitrev_n(p)) mod N ; 2: scatter to leaf owners
     uint64_t scale;                  // multiply at store when != 1 (1/N for the iFFT)
+    // store_mode 2 (multi-GPU, last pass of a coset): row p of this coset is leaf row  scatter_row0 + p  of the global
+    // leaf matrix; its owner is rank (row >> log_rows_per_peer) and the 8-column segment goes straight into that rank's
+    // leaf buffer (peer pointer over NVLink, or local) at columns [scatter_col0, ...): the column->row exchange is
+    // the NTT's own store, there is no all-to-all and no repacking.
+    uint64_t* peer[MAX_PEERS];
+    uint64_t scatter_row0;
+    uint32_t log_rows_per_peer, scatter_col0, scatter_pitch, scatter_ncols;   // padding columns (>= ncols) are not stored
 };
 
 __device__ __forceinline__ uint32_t ins3(uint32_t q, uint32_t sh, uint32_t e) {
@@ -165,16 +174,29 @@ __global__ void ntt_pass_kernel(const PassParams p) {
         if (p.scale != 1) v = gl::mul(v, p.scale);
         v = gl::canon(v);
         uint32_t prow = row_base | (l << b_lo);
-        uint32_t drow = p.store_mode == 1 ? ((N - gl::bitrev32(prow, p.log_n)) & (N - 1)) : prow;
-        p.dst[(uint64_t)drow * p.dst_pitch + col] = v;
+        if (p.store_mode == 2) {
+            if (col >= p.scatter_ncols) continue;
+            const uint64_t grow = p.scatter_row0 + prow;
+            uint64_t* base = p.peer[grow >> p.log_rows_per_peer];
+            base[(grow & ((1ULL << p.log_rows_per_peer) - 1)) * p.scatter_pitch + p.scatter_col0 + col] = v;
+        } else {
+            uint32_t drow = p.store_mode == 1 ? ((N - gl::bitrev32(prow, p.log_n)) & (N - 1)) : prow;
+            p.dst[(uint64_t)drow * p.dst_pitch + col] = v;
+        }
     }
 }
 
 // NTT sizes 1, 2, 4 (log_n < 3): direct O(N^2) evaluation, one thread per (output row, column).
 // Produces the same in-place-DIF order (row p holds X[bitrev(p)]) / iFFT order as the pass kernel.
+struct Scatter {   // see PassParams
+    uint64_t* peer[MAX_PEERS];
+    uint64_t row0;
+    uint32_t log_rows_per_peer, col0, pitch, ncols;
+};
+
 __global__ void ntt_tiny_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint32_t src_pitch,
                                 uint32_t dst_pitch, uint32_t n_cols, uint32_t log_n, uint64_t root, uint64_t g,
-                                uint32_t store_mode, uint64_t scale) {
+                                uint32_t store_mode, uint64_t scale, const Scatter sc) {
     const uint32_t N = 1u << log_n;
     uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t p = blockIdx.y;
@@ -189,6 +211,12 @@ __global__ void ntt_tiny_kernel(const uint64_t* __restrict__ src, uint64_t* __re
         cur = gl::mulc(cur, step);
     }
     if (scale != 1) acc = gl::mulc(acc, scale);
+    if (store_mode == 2) {
+        if (col >= sc.ncols) return;
+        const uint64_t grow = sc.row0 + p;
+        sc.peer[grow >> sc.log_rows_per_peer][(grow & ((1ULL << sc.log_rows_per_peer) - 1)) * sc.pitch + sc.col0 + col] = acc;
+        return;
+    }
     uint32_t drow = store_mode == 1 ? ((N - k) & (N - 1)) : p;
     dst[(uint64_t)drow * dst_pitch + col] = acc;
 }

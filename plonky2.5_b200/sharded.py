@@ -75,22 +75,68 @@ def exchange_reference(plan: ShardPlan, shards: List[np.ndarray]) -> List[np.nda
 
 
 class ShardedCommit:
-    """Device buffers + the four steps above for one rank.  Buffers are allocated once and reused by every commit."""
+    """Device buffers + the four steps above for one rank.  Buffers are allocated once and reused by every commit.
 
-    def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch):
+    exchange="p2p" (default when the ranks can map each other's memory): steps 1 and 2 are ONE kernel sequence — the last
+    NTT pass of every coset stores each 64-byte leaf-row segment straight into the owner's leaf buffer over NVLink
+    (gl_dev_lde_scatter; buffers exported/mapped with CUDA IPC), so there is no all-to-all, no receive buffer and no
+    repacking; the ranks only meet at a barrier before hashing.  exchange="nccl": gl_dev_lde + all_to_all_single +
+    gl_dev_repack (the baseline the fused path is measured against)."""
+
+    def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch, exchange: str = "p2p"):
         self.ctx, self.plan, self.rank, self.dist, self.torch = ctx, plan, rank, dist, torch
         dev = torch.device("cuda", ctx.device)
         p = plan
         i64 = torch.int64
-        self.rows = torch.empty(p.n_rows * p.pitches[rank], dtype=i64, device=dev)          # [R][pitch_g]
+        self.exchange = exchange
         self.coeffs = torch.empty((1 << p.log_n) * p.pitches[rank], dtype=i64, device=dev)  # [N][pitch_g]
-        self.recv = torch.empty(sum(p.recv_splits(rank)), dtype=i64, device=dev)
-        self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=i64, device=dev)    # [R/G][leaf_pitch]
         self.digests = torch.empty(max(p.digests_per_rank() * 4, 1), dtype=i64, device=dev)
         self.cap_local = np.zeros(4 << p.local_cap_height, dtype=np.uint64)
         self.cap_dev = torch.empty(4 << p.local_cap_height, dtype=i64, device=dev)
         self.cap_all = torch.empty(4 << p.cap_height, dtype=i64, device=dev)
         self.exchange_ms = 0.0
+        self._peer_ptrs = None
+        if exchange == "p2p":
+            self._init_p2p(dev)
+            return
+        self.rows = torch.empty(p.n_rows * p.pitches[rank], dtype=i64, device=dev)          # [R][pitch_g]
+        self.recv = torch.empty(sum(p.recv_splits(rank)), dtype=i64, device=dev)
+        self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=i64, device=dev)    # [R/G][leaf_pitch]
+        self.leaves_ptr = self.leaves.data_ptr()
+
+    def _init_p2p(self, dev):
+        p, lib, h, torch, dist = self.plan, self.ctx.lib, self.ctx.handle, self.torch, self.dist
+        words = p.rows_per_rank * p.leaf_pitch
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        self._check(lib.gl_dev_ipc_alloc(h, words, ctypes.byref(own), handle))
+        self.leaves_ptr = own.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        allh = torch.empty(64 * p.world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().reshape(p.world, 64)
+        ptrs = []
+        for q in range(p.world):
+            if q == self.rank:
+                ptrs.append(own.value)
+            else:
+                hq = (ctypes.c_uint8 * 64)(*allh[q].tolist())
+                pq = ctypes.c_void_p()
+                self._check(lib.gl_dev_ipc_open(h, hq, ctypes.byref(pq)))
+                ptrs.append(pq.value)
+        self._peer_ptrs = (ctypes.c_void_p * p.world)(*ptrs)
+        dist.barrier()
+
+    def close(self):
+        if self._peer_ptrs is not None:
+            lib, h = self.ctx.lib, self.ctx.handle
+            self.dist.barrier()
+            for q, ptr in enumerate(self._peer_ptrs):
+                if q != self.rank:
+                    lib.gl_dev_ipc_close(h, ptr)
+            self.dist.barrier()
+            lib.gl_dev_ipc_free(h, self.leaves_ptr)
+            self._peer_ptrs = None
 
     def _check(self, rc):
         if rc != 0:
@@ -102,6 +148,13 @@ class ShardedCommit:
         n = 1 << p.log_n
         ncg = p.col_counts[self.rank]
         assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
+        if self.exchange == "p2p":
+            # everyone must be done READING its leaf buffer (previous commit's hashing) before anyone writes into it again
+            self.dist.barrier()
+            self._check(lib.gl_dev_lde_scatter(h, d_cols.data_ptr(), n, ncg, p.log_n, p.rate_bits, 0, self._peer_ptrs, p.world,
+                                               p.leaf_pitch, p.col_offsets[self.rank], self.coeffs.data_ptr(), p.pitches[self.rank]))
+            self.dist.barrier()      # all peers' stores have landed (each rank synchronised its stream before the barrier)
+            return self._hash()
         self._check(lib.gl_dev_lde(h, d_cols.data_ptr(), n, ncg, p.log_n, p.rate_bits, 0, self.rows.data_ptr(), p.pitches[self.rank],
                                    self.coeffs.data_ptr()))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -113,9 +166,13 @@ class ShardedCommit:
         off = 0
         for q in range(p.world):
             self._check(lib.gl_dev_repack(h, self.recv.data_ptr() + 8 * off, p.pitches[q], p.col_counts[q], p.rows_per_rank,
-                                          self.leaves.data_ptr(), p.leaf_pitch, p.col_offsets[q]))
+                                          self.leaves_ptr, p.leaf_pitch, p.col_offsets[q]))
             off += p.rows_per_rank * p.pitches[q]
-        self._check(lib.gl_dev_merkle(h, self.leaves.data_ptr(), p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
+        return self._hash()
+
+    def _hash(self) -> np.ndarray:
+        p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
+        self._check(lib.gl_dev_merkle(h, self.leaves_ptr, p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
                                       self.digests.data_ptr(), self.cap_local.ctypes.data))
         self.cap_dev.copy_(torch.from_numpy(self.cap_local.view(np.int64)))
         self.dist.all_gather_into_tensor(self.cap_all, self.cap_dev)

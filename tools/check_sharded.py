@@ -34,17 +34,20 @@ def main():
         plan = ShardPlan(cols, log_n, r, h, world)
         c0, c1 = plan.col_range(rank)
         d = torch.from_numpy(x[c0:c1].view(np.int64).copy()).to(dev)
-        sc = ShardedCommit(ctx, plan, rank, dist, torch)
-        cap = sc.commit(d).reshape(-1, 4)
-        dig = sc.digests.cpu().numpy().view(np.uint64)[:plan.digests_per_rank() * 4].reshape(-1, 4)
-        want_dig = ref["digests"][rank * plan.digests_per_rank():(rank + 1) * plan.digests_per_rank()]
-        good = np.array_equal(cap, ref["cap"]) and np.array_equal(dig, want_dig)
-        # single-GPU product path on rank 0 agrees too
-        if rank == 0:
-            pb = g.PolynomialBatch.from_values(list(x), r, False, h, ctx=ctx)
-            good = good and np.array_equal(pb.merkle_tree.cap.hashes, cap)
-        print(f"rank {rank} shape {(log_n, cols, r, h)} world {world}: {'ok' if good else 'MISMATCH'} exchange {sc.exchange_ms:.3f} ms", flush=True)
-        ok = ok and good
+        for mode in ("p2p", "nccl"):
+            sc = ShardedCommit(ctx, plan, rank, dist, torch, exchange=mode)
+            cap = sc.commit(d).reshape(-1, 4)
+            cap2 = sc.commit(d).reshape(-1, 4)          # buffers are reused: a second commit must give the same cap
+            dig = sc.digests.cpu().numpy().view(np.uint64)[:plan.digests_per_rank() * 4].reshape(-1, 4)
+            want_dig = ref["digests"][rank * plan.digests_per_rank():(rank + 1) * plan.digests_per_rank()]
+            good = np.array_equal(cap, ref["cap"]) and np.array_equal(cap2, ref["cap"]) and np.array_equal(dig, want_dig)
+            # single-GPU product path on rank 0 agrees too
+            if rank == 0:
+                pb = g.PolynomialBatch.from_values(list(x), r, False, h, ctx=ctx)
+                good = good and np.array_equal(pb.merkle_tree.cap.hashes, cap)
+            print(f"rank {rank} shape {(log_n, cols, r, h)} world {world} {mode}: {'ok' if good else 'MISMATCH'}", flush=True)
+            ok = ok and good
+            sc.close()
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
