@@ -201,7 +201,7 @@ __device__ __forceinline__ void normalize_limbs(double& L, double& H) {
     L = __fma_rn(cL, -B32, L);
     H = __dadd_rn(H, cL);
     const double cH = __dsub_rn(__fma_rn(H, INV32, MAGIC), MAGIC);   // cH * 2^64 = cH * (2^32 - 1)
-    H = __dadd_rn(__fma_rn(cH, -B32, H), cH);
+    H = __fma_rn(cH, -(B32 - 1.0), H);                               // H - cH*2^32 + cH, one exact operation
     L = __dsub_rn(L, cH);
 }
 
