@@ -109,6 +109,14 @@ int gl_fri_fold(gl_ctx* ctx, gl_handle fri, const uint64_t beta[2]);
 int gl_fri_final_poly(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* out_len);
 int gl_fri_end(gl_ctx* ctx, gl_handle fri);
 
+/* ---- FRI proof of work: fri_proof_of_work  (plonky2 fri/prover.rs) ---------------------------------------------
+ * sponge_state / input_buffer: the caller's Challenger fields (sponge_state, pending input_buffer, n_inputs < 8).
+ * Finds the SMALLEST canonical w such that, with the pending inputs written into the state and w in the next input
+ * lane, permute(state)[7] has >= min_leading_zeros leading zero bits (= what the serial `find` of the reference build,
+ * plonky2 `parallel` off, returns; deterministic).  The caller then observes w and draws the response as upstream. */
+int gl_fri_pow(gl_ctx* ctx, const uint64_t sponge_state[12], const uint64_t* input_buffer, uint32_t n_inputs,
+               uint32_t min_leading_zeros, uint64_t* out_witness);
+
 /* ---- Poseidon permutation batch (plonky2 hash/poseidon.rs · PoseidonPermutation::permute) ---------------------
  * states: n x 12 words, permuted in place, canonical on return.  Used by the host-side Challenger mirror.       */
 int gl_poseidon_permute(gl_ctx* ctx, uint64_t* states, uint64_t n);

@@ -454,6 +454,28 @@ class Challenger:
         self.output_buffer = list(self.sponge_state[:SPONGE_RATE])
 
 
+def fri_proof_of_work(challenger: "Challenger", min_leading_zeros: int) -> int:
+    """plonky2 fri/prover.rs · fri_proof_of_work, smallest witness (serial `find`, as the reference ships
+    plonky2 with `parallel` off).  Advances the challenger exactly as upstream (observe witness, draw the response)."""
+    base = list(challenger.sponge_state)
+    for i, v in enumerate(challenger.input_buffer):
+        base[i] = v
+    pos = len(challenger.input_buffer)
+    assert pos < SPONGE_RATE
+    w = 0
+    while True:
+        st = list(base)
+        st[pos] = w
+        r = poseidon(st)[SPONGE_RATE - 1]
+        if 64 - r.bit_length() >= min_leading_zeros:
+            break
+        w += 1
+    challenger.observe_element(w)
+    resp = challenger.get_challenge()
+    assert resp == r
+    return w
+
+
 # --------------------------------------------------------------------------------------------------------
 # A.7 FRI commit phase (plonky2/src/fri/prover.rs · fri_committed_trees; fri/reduction_strategies.rs;
 #     plonk/plonk_common.rs · reduce_with_powers)

@@ -317,6 +317,21 @@ class Challenger:
         self.output_buffer = [int(x) for x in self.sponge_state[:SPONGE_RATE]]
 
 
+def fri_proof_of_work(challenger: Challenger, min_leading_zeros: int, ctx: Optional[Context] = None) -> int:
+    """plonky2 fri/prover.rs · fri_proof_of_work: grind on the GPU for the smallest witness, then advance the transcript
+    exactly as upstream (observe the witness, draw the response and check its leading zeros)."""
+    ctx = ctx or challenger.ctx
+    st = np.ascontiguousarray(challenger.sponge_state, dtype=np.uint64)
+    buf = np.array(challenger.input_buffer, dtype=np.uint64)
+    w = c_uint64()
+    _check(ctx, ctx.lib.gl_fri_pow(ctx.handle, _ptr(st), _ptr(buf) if buf.size else None, buf.size, min_leading_zeros, byref(w)))
+    challenger.observe_element(w.value)
+    resp = challenger.get_challenge()
+    if 64 - int(resp).bit_length() < min_leading_zeros:
+        raise GlError("proof-of-work response does not have the required leading zeros")
+    return w.value
+
+
 class FriParams:
     """The fields of plonky2 fri/mod.rs · FriParams that fri_committed_trees reads."""
 

@@ -1002,6 +1002,37 @@ int gl_field_op(gl_ctx* c, int op, const uint64_t* a, const uint64_t* b, uint64_
     GL_API_END(c)
 }
 
+int gl_fri_pow(gl_ctx* c, const uint64_t sponge_state[12], const uint64_t* input_buffer, uint32_t n_inputs, uint32_t min_leading_zeros,
+               uint64_t* out_witness) {
+    GL_API_BEGIN(c)
+    if (!sponge_state || !out_witness || (n_inputs && !input_buffer)) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_inputs >= 8) GL_THROW(GL_ERR_INVALID, "input buffer must hold fewer than SPONGE_RATE = 8 elements");
+    if (min_leading_zeros > 40) GL_THROW(GL_ERR_UNSUPPORTED, "min_leading_zeros = %u: search space too large", min_leading_zeros);
+    uint64_t st[12];
+    for (int i = 0; i < 12; i++) st[i] = gl::canon(sponge_state[i]);
+    for (uint32_t i = 0; i < n_inputs; i++) st[i] = gl::canon(input_buffer[i]);
+    c->scratch.ensure(16);
+    unsigned long long* d_best = reinterpret_cast<unsigned long long*>(c->scratch.p + 12);
+    const unsigned long long none = ~0ULL;
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p, st, sizeof st, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_best, &none, 8, cudaMemcpyHostToDevice, c->stream));
+    // windows grow geometrically from ~4x the expected number of tries; every candidate below a window was rejected
+    uint64_t window = std::max<uint64_t>(1ULL << 16, 4ULL << min_leading_zeros);
+    window = std::min<uint64_t>(window, 1ULL << 28);
+    for (uint64_t base = 0;; base += window) {
+        if (base >= gl::P) GL_THROW(GL_ERR_INVALID, "no proof-of-work witness exists");
+        merkle::pow_grind_kernel<<<(uint32_t)((window + 127) / 128), 128, 0, c->stream>>>(c->scratch.p, n_inputs, min_leading_zeros, base,
+                                                                                        window, d_best);
+        CUDA_CHECK(cudaGetLastError());
+        unsigned long long best = none;
+        CUDA_CHECK(cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (best != none) { *out_witness = best; break; }
+    }
+    return GL_OK;
+    GL_API_END(c)
+}
+
 int gl_ctx_stage_times(gl_ctx* c, float* out_ms, uint32_t* out_launches) {
     if (!c || !out_ms) return GL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);

@@ -92,4 +92,23 @@ __global__ void permute_kernel(uint64_t* __restrict__ states, uint64_t n) {
     for (int k = 0; k < poseidon::WIDTH; k++) states[12 * i + k] = gl::canon(s[k]);
 }
 
+// K8: FRI proof-of-work grinding (plonky2 fri/prover.rs · fri_proof_of_work).  Candidate w goes to lane
+// `pos` of the pre-absorbed sponge state, one permutation, accept when canonical state[7] has >= min_lz leading zero
+// bits.  One thread per candidate of the window [base, base + n); the smallest accepted candidate wins (atomicMin), which
+// is the serial `find` the reference runs (plonky2 `parallel` off) and keeps the proof deterministic.
+__global__ void pow_grind_kernel(const uint64_t* __restrict__ state12, uint32_t pos, uint32_t min_lz, uint64_t base, uint64_t n,
+                                 unsigned long long* __restrict__ best) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t w = base + i;
+    if (w >= gl::P) return;                      // candidates are canonical field elements
+    uint64_t s[poseidon::WIDTH];
+#pragma unroll
+    for (int k = 0; k < poseidon::WIDTH; k++) s[k] = (uint32_t)k == pos ? w : state12[k];
+    poseidon::permute(s);
+    const uint64_t r = gl::canon(s[poseidon::RATE - 1]);
+    const uint32_t lz = r ? (uint32_t)__clzll((long long)r) : 64u;
+    if (lz >= min_lz) atomicMin(best, (unsigned long long)w);
+}
+
 }  // namespace merkle

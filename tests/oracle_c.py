@@ -59,6 +59,8 @@ class OracleC:
         L.glo_fri_committed_trees.restype = ctypes.c_int
         L.glo_fri_committed_trees.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp,
                                               ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+        L.glo_fri_proof_of_work.restype = u64
+        L.glo_fri_proof_of_work.argtypes = [vp, ctypes.c_uint32]
         L.glo_num_threads.restype = ctypes.c_int
         L.glo_root_of_unity.restype = u64
         L.glo_root_of_unity.argtypes = [ctypes.c_uint]
@@ -194,3 +196,6 @@ class ChallengerC:
         c0 = self.get_challenge()
         c1 = self.get_challenge()
         return (c0, c1)
+
+    def fri_proof_of_work(self, min_leading_zeros):
+        return int(self.oc.lib.glo_fri_proof_of_work(self.buf, min_leading_zeros))

@@ -257,3 +257,18 @@ def test_field_primitives_on_adversarial_words(ctx):
         got = ctx.field_op(op, a, b).tolist()
         bad = [i for i, (g_, w_) in enumerate(zip(got, want[name])) if g_ != w_]
         assert not bad, f"{name}: {len(bad)} mismatches, first a={ai[bad[0]]:#x} b={bi[bad[0]]:#x} got={got[bad[0]]:#x} want={want[name][bad[0]]:#x}"
+
+
+@pytest.mark.parametrize("bits", [0, 5, 12, 16, 20])
+def test_fri_proof_of_work_matches_oracle(ctx, oc, bits):
+    """gl_fri_pow (wrapper proof uses 16 bits) against the C restatement: same smallest witness, same transcript after."""
+    g = _g()
+    rng = random.Random(bits)
+    a, b = g.Challenger(ctx), oc.new_challenger()
+    es = [rng.randrange(P) for _ in range(bits % 7)]
+    a.observe_elements(es)
+    b.observe_elements(es)
+    wa = g.fri_proof_of_work(a, bits, ctx=ctx)
+    wb = b.fri_proof_of_work(bits)
+    assert wa == wb
+    assert a.get_challenge() == b.get_challenge()

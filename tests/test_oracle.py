@@ -223,3 +223,25 @@ def test_reduction_arity_bits_standard_recursion():
     # ConstantArityBits(4, 5), rate_bits 3, cap_height 4 (standard_recursion_config, src/p3/mod.rs:231)
     assert o.reduction_arity_bits_constant(4, 5, 16, 3, 4) == [4, 4, 4]
     assert o.reduction_arity_bits_constant(4, 5, 13, 3, 4) == [4, 4]
+
+
+def test_pow_c_matches_python_and_is_smallest(oc):
+    """fri_proof_of_work: C restatement == Python restatement, the witness is the smallest one, transcript advances alike."""
+    import random
+    rng = random.Random(4)
+    for bits in (0, 3, 7, 9):
+        a, b = o.Challenger(), oc.new_challenger()
+        es = [rng.randrange(o.P) for _ in range(rng.randrange(0, 7))]
+        a.observe_elements(es)
+        b.observe_elements(es)
+        base = list(a.sponge_state)
+        for i, v in enumerate(a.input_buffer):
+            base[i] = v
+        pos = len(a.input_buffer)
+        wa = o.fri_proof_of_work(a, bits)
+        wb = b.fri_proof_of_work(bits)
+        assert wa == wb
+        for w in range(wa):      # nothing smaller qualifies
+            st = list(base); st[pos] = w
+            assert 64 - o.poseidon(st)[7].bit_length() < bits
+        assert a.get_challenge() == b.get_challenge()
