@@ -127,9 +127,9 @@ std::vector<uint32_t> plan_passes(uint32_t n) {
     return v;
 }
 
-struct CosetTable {   // pre-scale factors g^j split as g^(l << (n - a1)) * g^(o_lo) for the first pass
+struct CosetTable {   // pre-scale factors g^j, j < N, fused into the first pass's loads
     uint64_t g = 1;
-    DevBuf A, B;
+    DevBuf F;
 };
 
 struct Tree {
@@ -190,18 +190,12 @@ const uint64_t* get_roots(gl_ctx* c, uint32_t log_n) {
 
 void fill_coset_table(gl_ctx* c, CosetTable& t, uint64_t g, uint32_t log_n) {
     t.g = g;
-    auto passes = plan_passes(log_n);
-    if (passes.empty()) return;
-    uint32_t a1 = passes[0], b = log_n - a1;
-    std::vector<uint64_t> A((size_t)1 << a1), B((size_t)1 << b);
-    uint64_t gb = gl::h_pow(g, 1ULL << b), cur = 1;
-    for (auto& x : A) { x = cur; cur = gl::h_mul(cur, gb); }
-    cur = 1;
-    for (auto& x : B) { x = cur; cur = gl::h_mul(cur, g); }
-    t.A.ensure(A.size());
-    t.B.ensure(B.size());
-    CUDA_CHECK(cudaMemcpyAsync(t.A.p, A.data(), A.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(t.B.p, B.data(), B.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    if (log_n < 3) return;   // ntt_tiny_kernel takes g itself
+    std::vector<uint64_t> F((size_t)1 << log_n);
+    uint64_t cur = 1;
+    for (auto& x : F) { x = cur; cur = gl::h_mul(cur, g); }
+    t.F.ensure(F.size());
+    CUDA_CHECK(cudaMemcpyAsync(t.F.p, F.data(), F.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
@@ -263,8 +257,7 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
         p.log_blk = log_blk;
         p.a = passes[i];
         p.W = W;
-        p.preA = (first && pre) ? pre->A.p : nullptr;
-        p.preB = (first && pre) ? pre->B.p : nullptr;
+        p.pre = (first && pre) ? pre->F.p : nullptr;
         p.store_mode = (ifft && last) ? 1 : 0;
         p.scale = (ifft && last) ? n_inv : 1;
         if (scatter && last) {

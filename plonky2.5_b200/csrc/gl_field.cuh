@@ -88,10 +88,24 @@ __device__ __forceinline__ void mul_words(uint64_t a, uint64_t b, uint32_t& z0, 
         "}" : "=&r"(z0), "=&r"(z1), "=&r"(z2), "=&r"(z3)
             : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
 }
+// The same product through nvcc's 128-bit multiply (mul.lo.u64 + mul.hi.u64): ptxas then uses the carry-out / carry-in
+// forms of IMAD.WIDE.U32 (which PTX cannot name), 4 IMAD.WIDE + IMAD.X + MOV + 1 IADD3 — one alu-pipe instruction
+// instead of five.  Which form is faster depends on which pipe the surrounding code saturates.
+__device__ __forceinline__ void mul_words_c(uint64_t a, uint64_t b, uint32_t& z0, uint32_t& z1, uint32_t& z2, uint32_t& z3) {
+    const uint64_t lo = a * b, hi = __umul64hi(a, b);
+    z0 = (uint32_t)lo; z1 = (uint32_t)(lo >> 32); z2 = (uint32_t)hi; z3 = (uint32_t)(hi >> 32);
+}
+#ifndef GL_MUL_NEW
+#define GL_MUL_NEW 1
+#endif
 // "any" in, "any" out
 __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
     uint32_t z0, z1, z2, z3;
+#if GL_MUL_NEW
+    mul_words_c(a, b, z0, z1, z2, z3);
+#else
     mul_words(a, b, z0, z1, z2, z3);
+#endif
 #ifdef GL_REDUCE_MADWIDE
     return reduce_words_madwide(z0, z1, z2, z3);
 #else

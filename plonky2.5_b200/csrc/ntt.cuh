@@ -32,8 +32,7 @@ struct PassParams {
     uint32_t a;                      // stages done in this pass (>= 3)
     uint32_t ncg;                    // column groups (pitch / G)
     const uint64_t* W;               // w_N^e, e < max(N/2, 1), canonical
-    const uint64_t* preA;            // coset pre-scale (first pass only) g^(l << (log_n-a)), l < 2^a, or nullptr
-    const uint64_t* preB;            //                                   g^(o_lo), o_lo < 2^(log_n-a)
+    const uint64_t* pre;             // coset pre-scale (first pass only): g^row, row < N, or nullptr
     uint32_t store_mode;             // 0: row p -> p ; 1: iFFT: row p -> (N - bitrev_n(p)) mod N ; 2: scatter to leaf owners
     uint64_t scale;                  // multiply at store when != 1 (1/N for the iFFT)
     // store_mode 2 (multi-GPU, last pass of a coset): row p of this coset is leaf row  scatter_row0 + p  of the global
@@ -126,19 +125,13 @@ __global__ void ntt_pass_kernel(const PassParams p) {
     uint64_t x[8];
     uint32_t sh = a - 3;
     {
-        uint64_t bv = 1;
-        const bool pre = p.preA != nullptr;
-        if (pre && b_lo) bv = p.preB[o_lo];
+        const bool pre = p.pre != nullptr;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             uint32_t l = ins3(q, sh, e);
             uint64_t row = row_base | ((uint64_t)l << b_lo);
             uint64_t v = p.src[row * p.src_pitch + col];
-            if (pre) {
-                uint64_t f = p.preA[l];
-                if (b_lo) f = gl::mul(f, bv);
-                v = gl::mul(v, f);
-            }
+            if (pre) v = gl::mul(v, __ldg(p.pre + row));
             x[e] = v;
         }
     }

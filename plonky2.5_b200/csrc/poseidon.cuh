@@ -26,11 +26,35 @@ constexpr int N_FULL_HALF = 4;
 constexpr int N_PARTIAL = 22;
 constexpr int N_ROUNDS = 30;
 
+// Per-product choice of the 128-bit product form inside the S-box (bit 0: x^2, bit 1: x^4, bit 2: x^3, bit 3: x^3*x^4):
+// 0 = PTX carry chains (3 IMAD.WIDE for a square, 6 alu adds), 1 = nvcc's 128-bit multiply (4 IMAD.WIDE, 1 alu add).
+// The full rounds are alu-pipe-bound with form 0 everywhere and fma-pipe-bound with form 1 everywhere.
+#ifndef POSEIDON_SBOX_FORM
+#define POSEIDON_SBOX_FORM 0x8
+#endif
+template <int NEW>
+__device__ __forceinline__ uint64_t sbox_sqr(uint64_t x) {
+    if (NEW) {
+        uint32_t z0, z1, z2, z3;
+        gl::mul_words_c(x, x, z0, z1, z2, z3);
+        return gl::reduce_words(z0, z1, z2, z3);
+    }
+    return gl::sqr(x);
+}
+template <int NEW>
+__device__ __forceinline__ void sbox_mul_words(uint64_t a, uint64_t b, uint32_t& z0, uint32_t& z1, uint32_t& z2, uint32_t& z3) {
+    if (NEW) gl::mul_words_c(a, b, z0, z1, z2, z3);
+    else gl::mul_words(a, b, z0, z1, z2, z3);
+}
+
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-    uint64_t x2 = gl::sqr(x);
-    uint64_t x4 = gl::sqr(x2);
-    uint64_t x3 = gl::mul(x, x2);
-    return gl::mul(x3, x4);
+    const uint64_t x2 = sbox_sqr<(POSEIDON_SBOX_FORM >> 0) & 1>(x);
+    const uint64_t x4 = sbox_sqr<(POSEIDON_SBOX_FORM >> 1) & 1>(x2);
+    uint32_t z0, z1, z2, z3;
+    sbox_mul_words<(POSEIDON_SBOX_FORM >> 2) & 1>(x, x2, z0, z1, z2, z3);
+    const uint64_t x3 = gl::reduce_words(z0, z1, z2, z3);
+    sbox_mul_words<(POSEIDON_SBOX_FORM >> 3) & 1>(x3, x4, z0, z1, z2, z3);
+    return gl::reduce_words(z0, z1, z2, z3);
 }
 
 constexpr double TWO52 = 4503599627370496.0;
@@ -44,11 +68,12 @@ __device__ __forceinline__ double limb_to_double(uint32_t w) { return __dsub_rn(
 // not reduced to 64 bits on the integer pipe: 2^64 = 2^32 - 1 and 2^96 = -1 give lo = z0 - z2 - z3 (signed, |lo| < 2^33)
 // and hi = z1 + z2 (< 2^33), six exact DADDs — cheaper than reduce_words + conversion, and off the alu pipe.
 __device__ __forceinline__ void sbox7_limbs(uint64_t x, double& lo, double& hi) {
-    const uint64_t x2 = gl::sqr(x);
-    const uint64_t x4 = gl::sqr(x2);
-    const uint64_t x3 = gl::mul(x, x2);
+    const uint64_t x2 = sbox_sqr<(POSEIDON_SBOX_FORM >> 0) & 1>(x);
+    const uint64_t x4 = sbox_sqr<(POSEIDON_SBOX_FORM >> 1) & 1>(x2);
     uint32_t z0, z1, z2, z3;
-    gl::mul_words(x3, x4, z0, z1, z2, z3);
+    sbox_mul_words<(POSEIDON_SBOX_FORM >> 2) & 1>(x, x2, z0, z1, z2, z3);
+    const uint64_t x3 = gl::reduce_words(z0, z1, z2, z3);
+    sbox_mul_words<(POSEIDON_SBOX_FORM >> 3) & 1>(x3, x4, z0, z1, z2, z3);
     const double d2 = biased(z2);
     lo = __dsub_rn(__dsub_rn(biased(z0), d2), __dsub_rn(biased(z3), TWO52));
     hi = __dsub_rn(__dadd_rn(biased(z1), __dsub_rn(d2, TWO52)), TWO52);
@@ -205,6 +230,7 @@ __device__ __forceinline__ void normalize_limbs(double& L, double& H) {
     L = __dsub_rn(L, cH);
 }
 
+#ifdef POSEIDON_PARTIAL_V3
 __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     double L[WIDTH], H[WIDTH];
 #pragma unroll
@@ -235,6 +261,136 @@ __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     for (int i = 1; i < WIDTH; i++)
         s[i] = recombine(__dadd_rn(L[i], POSEIDON_PARTIAL_TAIL[i - 1][0]), __dadd_rn(H[i], POSEIDON_PARTIAL_TAIL[i - 1][1]));
 }
+#else
+// ---- v4: the 11 resident lanes live in the CRT domain of the circulant ------------------------------------------------
+// With a_i, b_i, m_i as in mds_limb (cyclic-3, negacyclic-3, negacyclic-6 parts of one limb vector) the MDS layer acts
+// blockwise, a' = 4*UU(a), b' = 4*UV(b), m' = 2*V(m): the 30 add/sub butterflies of the time-domain layer disappear
+// when the state stays in this domain for all 22 partial rounds.  Lane 0 is read out as (a0 + b0 + 2 m0)/4 (an integer
+// identity) and written back by adding (y - lane0) to a0, b0, m0; the diagonal 8*s0 reaches a0', b0', m0'; the round
+// constant is only needed at the read-out.  Re-normalisation carries are multiples of 4, so the division by 4 stays
+// exact on each limb.  63 fp64 operations per limb and round instead of 89, and everything that does not depend on the
+// S-box output is off the dependency chain.  tools/mds_model.py · permute_v4 mirrors this operation by operation and
+// proves (by bound propagation) that no intermediate reaches 2^53.
+struct Freq {
+    double a[3], b[3], m[6];
+};
+
+// time -> CRT domain of lanes 1..11 (lane 0 enters as 0: it is replaced by the S-box output in the first round)
+__device__ __forceinline__ void freq_forward(const double (&s)[WIDTH], Freq& f) {
+    double sp[6];
+    sp[0] = s[6];
+    f.m[0] = -s[6];
+#pragma unroll
+    for (int i = 1; i < 6; i++) {
+        sp[i] = __dadd_rn(s[i], s[i + 6]);
+        f.m[i] = __dsub_rn(s[i], s[i + 6]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        f.a[i] = __dadd_rn(sp[i], sp[i + 3]);
+        f.b[i] = __dsub_rn(sp[i], sp[i + 3]);
+    }
+}
+
+// lane 0 (raw value e) <- y, then the MDS layer.  The component that carries y is the last link of every chain.
+__device__ __forceinline__ void freq_round(Freq& f, const double y, const double e) {
+    const double d = __dsub_rn(y, e);
+    const double a0 = __dadd_rn(f.a[0], d), b0 = __dadd_rn(f.b[0], d), m0 = __dadd_rn(f.m[0], d);
+    const double t1 = __dmul_rn(__dadd_rn(f.a[1], f.a[2]), 64.0);
+    const double na0 = __fma_rn(y, 8.0, __fma_rn(a0, 64.0, __fma_rn(f.a[2], 64.0, t1)));
+    const double na1 = __fma_rn(a0, 128.0, t1);
+    const double na2 = __fma_rn(a0, 64.0, __fma_rn(f.a[1], 64.0, t1));
+    const double nb0 = __fma_rn(y, 8.0, __fma_rn(b0, -4.0, __fma_rn(f.b[2], 32.0, __dmul_rn(f.b[1], -8.0))));
+    const double nb1 = __fma_rn(b0, -32.0, __fma_rn(f.b[1], -4.0, __dmul_rn(f.b[2], -8.0)));
+    const double nb2 = __fma_rn(b0, 8.0, __fma_rn(f.b[1], -32.0, __dmul_rn(f.b[2], -4.0)));
+    // negacyclic-6 with 2*[2, -4, 16, 1, -1, -1]: coefficient of m[j] in m'[n] is 2*f[n-j] (j <= n) or -2*f[6+n-j]
+    constexpr double g[6] = {4.0, -8.0, 32.0, 2.0, -2.0, -2.0};
+    double nm[6];
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+        double acc = __dmul_rn(f.m[1], (1 <= n) ? g[n - 1] : -g[5 + n]);
+#pragma unroll
+        for (int j = 2; j < 6; j++) acc = __fma_rn(f.m[j], (j <= n) ? g[n - j] : -g[6 + n - j], acc);
+        nm[n] = __fma_rn(m0, g[n], acc);
+    }
+    nm[0] = __fma_rn(y, 8.0, nm[0]);
+    f.a[0] = na0; f.a[1] = na1; f.a[2] = na2;
+    f.b[0] = nb0; f.b[1] = nb1; f.b[2] = nb2;
+#pragma unroll
+    for (int n = 0; n < 6; n++) f.m[n] = nm[n];
+}
+
+// raw lane-0 value (a0 + b0 + 2 m0)/4; 0.5*m0 is an exact half-integer, the result an exact integer
+__device__ __forceinline__ double freq_lane0(const Freq& f) {
+    return __fma_rn(__dadd_rn(f.a[0], f.b[0]), 0.25, __dmul_rn(f.m[0], 0.5));
+}
+
+// (L, H) with value L + H*2^32 -> same value mod p with |L|, |H| <= 2^33 + 2^20, carries multiples of 4 (inputs < 2^52)
+__device__ __forceinline__ void normalize_limbs4(double& L, double& H) {
+    constexpr double MAGIC4 = 27021597764222976.0;    // 1.5 * 2^54: adding it rounds to a multiple of 4
+    constexpr double INV32 = 2.3283064365386963e-10;  // 2^-32
+    constexpr double B32 = 4294967296.0;
+    const double cL = __dsub_rn(__fma_rn(L, INV32, MAGIC4), MAGIC4);
+    L = __fma_rn(cL, -B32, L);
+    H = __dadd_rn(H, cL);
+    const double cH = __dsub_rn(__fma_rn(H, INV32, MAGIC4), MAGIC4);   // cH * 2^64 = cH * (2^32 - 1)
+    H = __fma_rn(cH, -(B32 - 1.0), H);
+    L = __dsub_rn(L, cH);
+}
+
+__device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
+    Freq FL, FH;
+    {
+        double l[WIDTH], h[WIDTH];
+        l[0] = h[0] = 0.0;
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) {
+            l[i] = limb_to_double((uint32_t)s[i]);
+            h[i] = limb_to_double((uint32_t)(s[i] >> 32));
+        }
+        freq_forward(l, FL);
+        freq_forward(h, FH);
+    }
+    uint64_t x0 = s[0];
+    double eL = 0.0, eH = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < N_PARTIAL; r++) {
+        double yL, yH;
+        sbox7_limbs(x0, yL, yH);
+        freq_round(FL, yL, eL);
+        freq_round(FH, yH, eH);
+        if (r & 1) {   // rounds 5, 7, .., 25
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                normalize_limbs4(FL.a[i], FH.a[i]);
+                normalize_limbs4(FL.b[i], FH.b[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) normalize_limbs4(FL.m[i], FH.m[i]);
+        }
+        eL = freq_lane0(FL);
+        eH = freq_lane0(FH);
+        x0 = recombine(__dadd_rn(eL, POSEIDON_PARTIAL4_Q[r][0]), __dadd_rn(eH, POSEIDON_PARTIAL4_Q[r][1]));
+    }
+    s[0] = x0;
+    // back to the time domain: s_i = (a_i + b_i)/4 + m_i/2, s_{i+6} = (a_i + b_i)/4 - m_i/2, s_{i+3}, s_{i+9} with a_i - b_i
+    double l[WIDTH], h[WIDTH];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double tpl = __dadd_rn(FL.a[i], FL.b[i]), tml = __dsub_rn(FL.a[i], FL.b[i]);
+        const double tph = __dadd_rn(FH.a[i], FH.b[i]), tmh = __dsub_rn(FH.a[i], FH.b[i]);
+        const double ml = __dmul_rn(FL.m[i], 0.5), ml3 = __dmul_rn(FL.m[i + 3], 0.5);
+        const double mh = __dmul_rn(FH.m[i], 0.5), mh3 = __dmul_rn(FH.m[i + 3], 0.5);
+        l[i] = __fma_rn(tpl, 0.25, ml);      l[i + 6] = __fma_rn(tpl, 0.25, -ml);
+        l[i + 3] = __fma_rn(tml, 0.25, ml3); l[i + 9] = __fma_rn(tml, 0.25, -ml3);
+        h[i] = __fma_rn(tph, 0.25, mh);      h[i + 6] = __fma_rn(tph, 0.25, -mh);
+        h[i + 3] = __fma_rn(tmh, 0.25, mh3); h[i + 9] = __fma_rn(tmh, 0.25, -mh3);
+    }
+#pragma unroll
+    for (int i = 1; i < WIDTH; i++)
+        s[i] = recombine(__dadd_rn(l[i], POSEIDON_PARTIAL4_TAIL[i - 1][0]), __dadd_rn(h[i], POSEIDON_PARTIAL4_TAIL[i - 1][1]));
+}
+#endif
 
 // Full permutation. in/out "any" -> "any" (callers canonicalise what they store).
 // One copy of the full-round body serves both halves (the code must stay inside the 32 KB L1.5 instruction cache).

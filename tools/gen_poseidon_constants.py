@@ -95,6 +95,19 @@ def mds_tables(rc):
     for i in range(11):
         cl, ch = rc_limbs(tail[i])
         txt += "    {%d.0, %d.0},\n" % (cl + OFF_LO + BIAS, ch + OFF_HI + BIAS)
+    txt += "};\n"
+    # v4: partial rounds in the CRT domain of the circulant (mds_model.permute_v4): the constant is added at read-out
+    from mds_model import OFF4_LO, OFF4_HI
+    txt += ("// PARTIAL4_Q[r-4][limb] = limb of the pushed-forward lane-0 constant of round r+1 + 2^52 + positivity offset (2^19 p split)\n"
+            "__constant__ double POSEIDON_PARTIAL4_Q[22][2] = {\n")
+    for r in range(4, 26):
+        cl, ch = rc_limbs(lane0[r + 1])
+        assert 0 <= cl + OFF4_LO < BIAS and 0 <= ch + OFF4_HI < BIAS
+        txt += "    {%d.0, %d.0},\n" % (cl + BIAS + OFF4_LO, ch + BIAS + OFF4_HI)
+    txt += "};\n// PARTIAL4_TAIL[i-1][limb]: as PARTIAL_TAIL with the v4 offsets\n__constant__ double POSEIDON_PARTIAL4_TAIL[11][2] = {\n"
+    for i in range(11):
+        cl, ch = rc_limbs(tail[i])
+        txt += "    {%d.0, %d.0},\n" % (cl + OFF4_LO + BIAS, ch + OFF4_HI + BIAS)
     return txt + "};\n"
 
 

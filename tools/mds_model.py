@@ -253,3 +253,189 @@ def selftest_v3():
 
 if __name__ == "__main__":
     selftest_v3()
+
+
+# ======================================================================================================================
+# v4: partial rounds in the CRT ("frequency") domain of the circulant
+# ======================================================================================================================
+# With a_i, b_i, m_i as in mds_limb (a = cyclic-3 part, b = negacyclic-3 part, m = negacyclic-6 part of one limb vector),
+# the MDS layer acts blockwise:  a' = 4*UU(a), b' = 4*UV(b), m' = 2*V(m)  — the 30 add/sub butterflies of the time-domain
+# layer disappear when the 11 resident lanes stay in this domain for all 22 partial rounds.  Lane 0 is read out as
+# (a0 + b0 + 2*m0)/4 (an integer identity) and written back by adding (y - lane0) to a0, b0, m0; the diagonal 8*s0 reaches
+# a0', b0', m0'.  Re-normalisation carries are multiples of 4 so that the division by 4 stays exact on each limb.
+OFF4_LO = (1 << 51) + (1 << 19)          # OFF4_LO + OFF4_HI*2^32 = 2^19 * p
+OFF4_HI = (1 << 51) - (1 << 20)
+assert OFF4_LO + (OFF4_HI << 32) == (1 << 19) * P
+
+
+class BV:
+    """exact integer value + proven bound on |value| (bounds are propagated through every operation: the asserts are a
+    proof that no intermediate reaches 2^53, not a test on sample inputs)."""
+    __slots__ = ("v", "m")
+
+    def __init__(self, v, m):
+        assert abs(v) <= m, (v, m)
+        assert m < (1 << 53), "fp64 exactness bound violated: 2^%.2f" % (m.bit_length())
+        self.v, self.m = v, m
+
+    def __add__(self, o): return BV(self.v + o.v, self.m + o.m)
+    def __sub__(self, o): return BV(self.v - o.v, self.m + o.m)
+    def scale(self, c): return BV(self.v * c, self.m * abs(c))
+    def fma(self, c, addend): return BV(self.v * c + addend.v, self.m * abs(c) + addend.m)   # self*c + addend
+
+
+def bv_const(c):
+    return BV(c, abs(c))
+
+
+def freq_forward(s):
+    sp = [s[i] + s[i + 6] for i in range(6)]; m = [s[i] - s[i + 6] for i in range(6)]
+    a = [sp[i] + sp[i + 3] for i in range(3)]; b = [sp[i] - sp[i + 3] for i in range(3)]
+    return a, b, m
+
+
+NEG6 = [[(F6[n - j] if j <= n else -F6[6 + n - j]) for j in range(6)] for n in range(6)]   # V[n] = sum_j m[j]*NEG6[n][j]
+
+
+def freq_round(a, b, m, y, e):
+    """One partial round on one limb: lane 0 (raw value e) is replaced by y, then the MDS layer.  Returns a', b', m'.
+    Mirrors csrc/poseidon.cuh · freq_round operation by operation (the component that carries y is last in every chain,
+    so everything else can be issued while the S-box is still running)."""
+    d = y - e
+    a0 = a[0] + d; b0 = b[0] + d; m0 = m[0] + d
+    t1 = (a[1] + a[2]).scale(64)
+    na = [y.fma(8, a0.fma(64, a[2].fma(64, t1))),
+          a0.fma(128, t1),
+          a0.fma(64, a[1].fma(64, t1))]
+    nb = [y.fma(8, b0.fma(-4, b[2].fma(32, b[1].scale(-8)))),
+          b0.fma(-32, b[1].fma(-4, b[2].scale(-8))),
+          b0.fma(8, b[1].fma(-32, b[2].scale(-4)))]
+    nm = []
+    for n in range(6):
+        acc = m[1].scale(2 * NEG6[n][1])
+        for j in range(2, 6):
+            acc = m[j].fma(2 * NEG6[n][j], acc)
+        acc = m0.fma(2 * NEG6[n][0], acc)
+        if n == 0:
+            acc = y.fma(8, acc)
+        nm.append(acc)
+    return na, nb, nm
+
+
+def freq_lane0(a, b, m):
+    """raw lane-0 value (a0 + b0 + 2*m0)/4: fma(a0 + b0, 0.25, 0.5*m0) — 0.5*m0 is an exact half-integer, the sum an integer"""
+    e4 = a[0].v + b[0].v + 2 * m[0].v
+    assert e4 % 4 == 0
+    return BV(e4 // 4, (a[0].m + b[0].m + 2 * m[0].m + 3) // 4)
+
+
+def rint4_div32(x):
+    """x / 2^32 rounded to a multiple of 4 (what (x*2^-32 + 1.5*2^54) - 1.5*2^54 computes in fp64: ulp at 2^54 is 4)"""
+    return 4 * rint_div(x, 34)
+
+
+def freq_normalize(L, H):
+    """(L, H) with value L + H*2^32 -> same value mod p, carries are multiples of 4; bounds are proven, not sampled:
+    |L - cL*2^32| <= 2^33, |cL| <= |L|/2^32 + 2, then |H1 - cH*2^32| <= 2^33 and |cH| <= |H1|/2^32 + 2."""
+    cL = rint4_div32(L.v); cLm = (L.m >> 32) + 2
+    L1 = BV(L.v - (cL << 32), 1 << 33)
+    H1 = BV(H.v + cL, H.m + cLm)
+    cH = rint4_div32(H1.v); cHm = (H1.m >> 32) + 2
+    H2 = BV(H1.v - (cH << 32) + cH, (1 << 33) + cHm)
+    L2 = BV(L1.v - cH, L1.m + cHm)
+    assert (L2.v + (H2.v << 32) - L.v - (H.v << 32)) % P == 0
+    return L2, H2
+
+
+def sbox_limbs_bv(x):
+    lo, hi = sbox_limbs(x)
+    return BV(lo, 1 << 33), BV(hi, 1 << 33)      # lo = z0 - z2 - z3 in (-2^33, 2^32), hi = z1 + z2 < 2^33
+
+
+def permute_v4(state, rc, stats=None):
+    """Mirror of csrc/poseidon.cuh · permute (v4) on exact integers with proven magnitude bounds."""
+    lane0_c, tail_c = partial_constants(rc)
+    s = [(state[i] + rc[i]) % P for i in range(12)]
+
+    def full_layer(lo, hi, r):
+        lanes = [rc[12 * (r + 1) + i] if r < 29 else 0 for i in range(12)]
+        limbs = [rc_limbs(c) for c in lanes]
+        out = []
+        for limb, ins, off in ((0, lo, OFF_LO), (1, hi, OFF_HI)):
+            k = [int(x) for x in fold_constants([l[limb] + BIAS + off for l in limbs])]
+            o = mds_limb_checked(ins, k)
+            assert all(BIAS <= x < 2 * BIAS for x in o)
+            out.append([x - BIAS for x in o])
+        return [(out[0][i] + (out[1][i] << 32)) % P for i in range(12)]
+
+    def full_round(s, r):
+        lo, hi = zip(*[sbox_limbs(x) for x in s])
+        return full_layer(list(lo), list(hi), r)
+
+    for r in range(0, 4):
+        s = full_round(s, r)
+    x0 = s[0]
+    zero = BV(0, 0)
+    fr = []                                   # per limb: [a, b, m]
+    for limb in (0, 1):
+        lanes = [zero] + [BV((v >> (32 * limb)) & 0xFFFFFFFF, (1 << 32) - 1) for v in s[1:]]
+        fr.append(list(freq_forward(lanes)))
+    e = [zero, zero]                          # raw lane-0 value of each limb (lane 0 is 0 in the initial transform)
+    for r in range(4, 26):
+        y = sbox_limbs_bv(x0)
+        for limb in (0, 1):
+            a, b, m = fr[limb]
+            fr[limb] = list(freq_round(a, b, m, y[limb], e[limb]))
+        if stats is not None:
+            stats["max_unnorm"] = max(stats.get("max_unnorm", 0), max(x.m for l in fr for part in l for x in part))
+        if r & 1:
+            for part in range(3):
+                for i in range(len(fr[0][part])):
+                    fr[0][part][i], fr[1][part][i] = freq_normalize(fr[0][part][i], fr[1][part][i])
+        xs = []
+        for limb in (0, 1):
+            e[limb] = freq_lane0(*fr[limb])
+            c = rc_limbs(lane0_c[r + 1])[limb]
+            X = e[limb] + bv_const(c + BIAS + (OFF4_LO, OFF4_HI)[limb])
+            assert BIAS <= X.v < 2 * BIAS and e[limb].m < (1 << 51), "lane 0 read-out window"
+            xs.append(X.v - BIAS)
+        x0 = (xs[0] + (xs[1] << 32)) % P
+    # leave the fp64 domain: inverse transform (exact: every component is F*(integer vector) + multiples of 4)
+    out = [x0]
+    lanes = [[None] * 12, [None] * 12]
+    for limb in (0, 1):
+        a, b, m = fr[limb]
+        for i in range(3):
+            tp, tm = a[i] + b[i], a[i] - b[i]
+            for (t, j) in ((tp, i), (tm, i + 3)):
+                for sign, lane in ((1, j), (-1, j + 6)):
+                    v4 = t.v + 2 * sign * m[j].v
+                    assert v4 % 4 == 0
+                    lanes[limb][lane] = BV(v4 // 4, (t.m + 2 * m[j].m + 3) // 4)
+    for i in range(1, 12):
+        cl, ch = rc_limbs(tail_c[i - 1])
+        al = lanes[0][i] + bv_const(cl + OFF4_LO + BIAS); ah = lanes[1][i] + bv_const(ch + OFF4_HI + BIAS)
+        assert BIAS <= al.v < 2 * BIAS and BIAS <= ah.v < 2 * BIAS
+        assert lanes[0][i].m < (1 << 51) and lanes[1][i].m < (1 << 51)
+        out.append(((al.v - BIAS) + ((ah.v - BIAS) << 32)) % P)
+    s = out
+    for r in range(26, 30):
+        s = full_round(s, r)
+    return s
+
+
+def selftest_v4():
+    import os, sys, random
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from gen_poseidon_constants import constants
+    rc = constants()
+    rnd = random.Random(7)
+    stats = {}
+    tests = [[0] * 12, list(range(12)), [P - 1] * 12] + [[rnd.randrange(P) for _ in range(12)] for _ in range(60)]
+    for st in tests:
+        assert permute_v4(st, rc, stats) == permute_naive(st, rc)
+    print("permute_v4 model ok; proven bound on resident components = 2^%.2f" % (stats["max_unnorm"].bit_length()))
+
+
+if __name__ == "__main__":
+    selftest_v4()
