@@ -356,7 +356,7 @@ def main():
             "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
             "config": {"workload": workload_name(a), "log_n": log_n, "n_cols": cols, "rate_bits": r, "cap_height": h,
                        "sharding": "none" if world == 1 else (f"columns/{world} -> " + ("NTT stores into peer leaf buffers over NVLink (fused)"
-                                                                                  if a.exchange == "p2p" else "NCCL all-to-all + repack")
+                                                                                  if state.exchange == "p2p" else "NCCL all-to-all + repack")
                                                              + f" -> leaf ranges/{world}"),
                        "l2": "inputs (%.2f GB) and leaves (%.2f GB) exceed the 126 MB L2; no flush needed" % (cols * n * 8 / 1e9, R * cols * 8 / 1e9),
                        "permutations_per_step": perms_per_commit(log_n, cols, r, h)},

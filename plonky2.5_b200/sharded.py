@@ -96,36 +96,53 @@ class ShardedCommit:
         self.cap_all = torch.empty(4 << p.cap_height, dtype=i64, device=dev)
         self.exchange_ms = 0.0
         self._peer_ptrs = None
-        if exchange == "p2p":
-            self._init_p2p(dev)
+        if exchange == "p2p" and self._init_p2p(dev):
             return
+        self.exchange = "nccl"      # requested, or the ranks cannot map each other's memory (all ranks agree on this)
         self.rows = torch.empty(p.n_rows * p.pitches[rank], dtype=i64, device=dev)          # [R][pitch_g]
         self.recv = torch.empty(sum(p.recv_splits(rank)), dtype=i64, device=dev)
         self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=i64, device=dev)    # [R/G][leaf_pitch]
         self.leaves_ptr = self.leaves.data_ptr()
 
-    def _init_p2p(self, dev):
+    def _init_p2p(self, dev) -> bool:
+        """Export this rank's leaf buffer and map every peer's (CUDA IPC).  Collective; returns False on EVERY rank if any
+        rank failed (no IPC in this container, no peer access), after releasing whatever was mapped."""
         p, lib, h, torch, dist = self.plan, self.ctx.lib, self.ctx.handle, self.torch, self.dist
         words = p.rows_per_rank * p.leaf_pitch
         own = ctypes.c_void_p()
         handle = (ctypes.c_uint8 * 64)()
-        self._check(lib.gl_dev_ipc_alloc(h, words, ctypes.byref(own), handle))
-        self.leaves_ptr = own.value
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
-        allh = torch.empty(64 * p.world, dtype=torch.uint8, device=dev)
+        ok = lib.gl_dev_ipc_alloc(h, words, ctypes.byref(own), handle) == 0
+        mine = torch.tensor(list(handle) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        allh = torch.empty(65 * p.world, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine)
-        allh = allh.cpu().numpy().reshape(p.world, 64)
-        ptrs = []
-        for q in range(p.world):
-            if q == self.rank:
-                ptrs.append(own.value)
-            else:
-                hq = (ctypes.c_uint8 * 64)(*allh[q].tolist())
+        allh = allh.cpu().numpy().reshape(p.world, 65)
+        ptrs, opened = [], []
+        ok = bool(allh[:, 64].all())
+        if ok:
+            for q in range(p.world):
+                if q == self.rank:
+                    ptrs.append(own.value)
+                    continue
+                hq = (ctypes.c_uint8 * 64)(*allh[q, :64].tolist())
                 pq = ctypes.c_void_p()
-                self._check(lib.gl_dev_ipc_open(h, hq, ctypes.byref(pq)))
+                if lib.gl_dev_ipc_open(h, hq, ctypes.byref(pq)) != 0:
+                    ok = False
+                    break
                 ptrs.append(pq.value)
+                opened.append(pq.value)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            for ptr in opened:
+                lib.gl_dev_ipc_close(h, ptr)
+            dist.barrier()
+            if own.value:
+                lib.gl_dev_ipc_free(h, own.value)
+            return False
+        self.leaves_ptr = own.value
         self._peer_ptrs = (ctypes.c_void_p * p.world)(*ptrs)
         dist.barrier()
+        return True
 
     def close(self):
         if self._peer_ptrs is not None:
