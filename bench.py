@@ -329,24 +329,27 @@ def main():
     roof = None
     if leaf_ms > 0:
         ach = alg_bytes / (leaf_ms * 1e-3) / 1e9
-        int_peak = None
-        try:
-            int_peak = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
-        except OSError:
-            pass
         roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": round(ach, 2), "peak": peak_gbs, "unit": "GB/s",
                 "frac": round(ach / peak_gbs, 5), "traffic": None, "peak_source": peak_src, "ms_per_launch": round(leaf_ms, 3),
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "hashing is bound by the SM integer/fp64 issue rate, not HBM (DESIGN.md §roofline): see int_pipe",
-                "int_pipe": {"permutations_per_s": round(perms_leaf / (leaf_ms * 1e-3), 1),
-                             "peak_permutations_per_s": (int_peak or {}).get("poseidon_perm_issue_bound_per_s"),
-                             "frac": (round(perms_leaf / (leaf_ms * 1e-3) / int_peak["poseidon_perm_issue_bound_per_s"], 4)
-                                      if int_peak and int_peak.get("poseidon_perm_issue_bound_per_s") else None)}}
+                "note": "hashing is bound by the SM instruction-issue/dispatch port, not HBM (DESIGN.md §4): `issue` is the binding roofline",
+                "issue": None}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "leaf_hash_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "leaf_hash_profile.json")))
+            if prof.get("cols") == cols:
+                # instructions per permutation are data-independent (branch-free code): ncu's smsp__inst_executed of one
+                # launch / its permutations; the peak is one warp instruction per SM sub-partition per clock
+                ipp = prof["warp_inst_per_launch"] / (prof["rows"] * ((cols + 7) // 8) / 32)
+                sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+                peak_issue = 148 * 4 * sm_mhz * 1e6
+                ach_issue = perms_leaf / 32 * ipp / (leaf_ms * 1e-3)
+                roof["issue"] = {"achieved_warp_inst_per_s": round(ach_issue, 1), "peak_warp_inst_per_s": peak_issue,
+                                 "frac": round(ach_issue / peak_issue, 4), "warp_inst_per_permutation": round(ipp, 1),
+                                 "permutations_per_s": round(perms_leaf / (leaf_ms * 1e-3), 1), "sm_mhz": sm_mhz,
+                                 "source": prof.get("source")}
             if prof.get("rows") == rows_local and prof.get("cols") == cols:
                 roof["traffic"] = prof["dram_bytes_per_launch"]
-        except OSError:
+        except (OSError, KeyError):
             pass
 
     cpu = None if a.no_cpu_baseline else cpu_baseline(a)
