@@ -74,9 +74,25 @@ __device__ __forceinline__ void sbox7_limbs(uint64_t x, double& lo, double& hi) 
     sbox_mul_words<(POSEIDON_SBOX_FORM >> 2) & 1>(x, x2, z0, z1, z2, z3);
     const uint64_t x3 = gl::reduce_words(z0, z1, z2, z3);
     sbox_mul_words<(POSEIDON_SBOX_FORM >> 3) & 1>(x3, x4, z0, z1, z2, z3);
+#ifdef POSEIDON_HANDOFF_FP64
     const double d2 = biased(z2);
     lo = __dsub_rn(__dsub_rn(biased(z0), d2), __dsub_rn(biased(z3), TWO52));
     hi = __dsub_rn(__dadd_rn(biased(z1), __dsub_rn(d2, TWO52)), TWO52);
+#else
+    // z0 - z2 - z3 + 2^33 and z1 + z2 are formed on the integer pipe directly in the mantissa of 2^52 + v (the borrows /
+    // the carry run into the high word 0x43300002 / 0x43300000), so each limb costs one DADD to remove the bias
+    uint32_t ll, lh, hl, hh;
+    asm("{\n\t"
+        "sub.cc.u32  %0, %4, %6;\n\t"
+        "subc.u32    %1, 0x43300002, 0;\n\t"
+        "sub.cc.u32  %0, %0, %7;\n\t"
+        "subc.u32    %1, %1, 0;\n\t"
+        "add.cc.u32  %2, %5, %6;\n\t"
+        "addc.u32    %3, 0x43300000, 0;\n\t"
+        "}" : "=&r"(ll), "=&r"(lh), "=&r"(hl), "=&r"(hh) : "r"(z0), "r"(z1), "r"(z2), "r"(z3));
+    lo = __dsub_rn(__hiloint2double((int)lh, (int)ll), TWO52 + 8589934592.0);
+    hi = __dsub_rn(__hiloint2double((int)hh, (int)hl), TWO52);
+#endif
 }
 
 // One limb of the MDS layer.  s[12]: exact integers (|s| < 2^41); k[12]: folded constants (uu0..2, uv0..2, v0..5);
@@ -230,7 +246,7 @@ __device__ __forceinline__ void normalize_limbs(double& L, double& H) {
     L = __dsub_rn(L, cH);
 }
 
-#ifdef POSEIDON_PARTIAL_V3
+#if defined(POSEIDON_PARTIAL_V3)
 __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     double L[WIDTH], H[WIDTH];
 #pragma unroll
@@ -261,7 +277,7 @@ __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
     for (int i = 1; i < WIDTH; i++)
         s[i] = recombine(__dadd_rn(L[i], POSEIDON_PARTIAL_TAIL[i - 1][0]), __dadd_rn(H[i], POSEIDON_PARTIAL_TAIL[i - 1][1]));
 }
-#else
+#elif defined(POSEIDON_PARTIAL_V4)
 // ---- v4: the 11 resident lanes live in the CRT domain of the circulant ------------------------------------------------
 // With a_i, b_i, m_i as in mds_limb (cyclic-3, negacyclic-3, negacyclic-6 parts of one limb vector) the MDS layer acts
 // blockwise, a' = 4*UU(a), b' = 4*UV(b), m' = 2*V(m): the 30 add/sub butterflies of the time-domain layer disappear
@@ -385,6 +401,168 @@ __device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
         l[i + 3] = __fma_rn(tml, 0.25, ml3); l[i + 9] = __fma_rn(tml, 0.25, -ml3);
         h[i] = __fma_rn(tph, 0.25, mh);      h[i + 6] = __fma_rn(tph, 0.25, -mh);
         h[i + 3] = __fma_rn(tmh, 0.25, mh3); h[i + 9] = __fma_rn(tmh, 0.25, -mh3);
+    }
+#pragma unroll
+    for (int i = 1; i < WIDTH; i++)
+        s[i] = recombine(__dadd_rn(l[i], POSEIDON_PARTIAL4_TAIL[i - 1][0]), __dadd_rn(h[i], POSEIDON_PARTIAL4_TAIL[i - 1][1]));
+}
+#else
+// ---- v5 = v4 with the negacyclic-6 part split once more: x^6+1 = (x^2+1)(x^4-x^2+1) ------------------------------------
+// As in v4 the 11 resident lanes live in the CRT domain of the circulant (a: cyclic-3, b: negacyclic-3; the MDS layer acts
+// blockwise, lane 0 is read out as (a0 + b0 + 2 m0)/4 and written back by adding (y - lane0) to the components that
+// contain it, the diagonal 8*s0 reaches the same components, carries are multiples of 4).  The negacyclic-6 part m is
+// kept as p = m mod (x^2+1) and q = m mod (x^4-x^2+1): m' = m*G becomes p' = p*(-30-12x) (4 products) and
+// q' = q*(6-6x+30x^2) (13 products) instead of 36.  The back-map divides by 3 (3 m0 = p0 + 2 q0 + q2): t/6 is rounded
+// to the nearest half-integer with a magic constant, which is exact because t is a multiple of 3; p and q carry in
+// multiples of 12 so that every limb stays divisible.  49 fp64 operations per limb and round (v4: 63, v3: 89).
+// tools/mds_model.py · permute_v5 mirrors this operation by operation and proves the 2^53 bounds.
+struct Freq5 {
+    double a[3], b[3], p[2], q[4];
+};
+
+__device__ __forceinline__ void freq5_forward(const double (&s)[WIDTH], Freq5& f) {
+    double sp[6], m[6];
+    sp[0] = s[6];
+    m[0] = -s[6];
+#pragma unroll
+    for (int i = 1; i < 6; i++) {
+        sp[i] = __dadd_rn(s[i], s[i + 6]);
+        m[i] = __dsub_rn(s[i], s[i + 6]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        f.a[i] = __dadd_rn(sp[i], sp[i + 3]);
+        f.b[i] = __dsub_rn(sp[i], sp[i + 3]);
+    }
+    f.p[0] = __dadd_rn(__dsub_rn(m[0], m[2]), m[4]);
+    f.p[1] = __dadd_rn(__dsub_rn(m[1], m[3]), m[5]);
+    f.q[0] = __dsub_rn(m[0], m[4]);
+    f.q[1] = __dsub_rn(m[1], m[5]);
+    f.q[2] = __dadd_rn(m[2], m[4]);
+    f.q[3] = __dadd_rn(m[3], m[5]);
+}
+
+// lane 0 (raw value e) <- y, then the MDS layer.  The component that carries y is the last link of every chain.
+__device__ __forceinline__ void freq5_round(Freq5& f, const double y, const double e) {
+    const double d = __dsub_rn(y, e);
+    const double a0 = __dadd_rn(f.a[0], d), b0 = __dadd_rn(f.b[0], d), p0 = __dadd_rn(f.p[0], d), q0 = __dadd_rn(f.q[0], d);
+    const double t1 = __dmul_rn(__dadd_rn(f.a[1], f.a[2]), 64.0);
+    const double na0 = __fma_rn(y, 8.0, __fma_rn(a0, 64.0, __fma_rn(f.a[2], 64.0, t1)));
+    const double na1 = __fma_rn(a0, 128.0, t1);
+    const double na2 = __fma_rn(a0, 64.0, __fma_rn(f.a[1], 64.0, t1));
+    const double nb0 = __fma_rn(y, 8.0, __fma_rn(b0, -4.0, __fma_rn(f.b[2], 32.0, __dmul_rn(f.b[1], -8.0))));
+    const double nb1 = __fma_rn(b0, -32.0, __fma_rn(f.b[1], -4.0, __dmul_rn(f.b[2], -8.0)));
+    const double nb2 = __fma_rn(b0, 8.0, __fma_rn(f.b[1], -32.0, __dmul_rn(f.b[2], -4.0)));
+    const double np0 = __fma_rn(y, 8.0, __fma_rn(p0, -30.0, __dmul_rn(f.p[1], 12.0)));
+    const double np1 = __fma_rn(p0, -12.0, __dmul_rn(f.p[1], -30.0));
+    const double nq0 = __fma_rn(y, 8.0, __fma_rn(q0, 6.0, __fma_rn(f.q[2], -30.0, __dmul_rn(f.q[3], 6.0))));
+    const double nq1 = __fma_rn(q0, -6.0, __fma_rn(f.q[1], 6.0, __dmul_rn(f.q[3], -30.0)));
+    const double nq2 = __fma_rn(q0, 30.0, __fma_rn(f.q[1], -6.0, __fma_rn(f.q[2], 36.0, __dmul_rn(f.q[3], -6.0))));
+    const double nq3 = __fma_rn(f.q[1], 30.0, __fma_rn(f.q[2], -6.0, __dmul_rn(f.q[3], 36.0)));
+    f.a[0] = na0; f.a[1] = na1; f.a[2] = na2;
+    f.b[0] = nb0; f.b[1] = nb1; f.b[2] = nb2;
+    f.p[0] = np0; f.p[1] = np1;
+    f.q[0] = nq0; f.q[1] = nq1; f.q[2] = nq2; f.q[3] = nq3;
+}
+
+constexpr double MAGIC_HALF = 3377699720527872.0;   // 1.5 * 2^51: adding it rounds to a multiple of 1/2
+constexpr double INV6 = 1.0 / 6.0;
+
+// t = 3 m  ->  m/2 (a half-integer), exact for |t| < 2^52
+__device__ __forceinline__ double third_half(double t) { return __dsub_rn(__fma_rn(t, INV6, MAGIC_HALF), MAGIC_HALF); }
+
+// raw lane-0 value (a0 + b0 + 2 m0)/4 with 3 m0 = p0 + 2 q0 + q2
+__device__ __forceinline__ double freq5_lane0(const Freq5& f) {
+    const double t = __fma_rn(f.q[0], 2.0, __dadd_rn(f.p[0], f.q[2]));
+    return __fma_rn(__dadd_rn(f.a[0], f.b[0]), 0.25, third_half(t));
+}
+
+// (L, H) with value L + H*2^32 -> same value mod p, carries multiples of 4 / of 12 (inputs < 2^52)
+__device__ __forceinline__ void normalize_limbs4(double& L, double& H) {
+    constexpr double MAGIC4 = 27021597764222976.0;    // 1.5 * 2^54: adding it rounds to a multiple of 4
+    constexpr double INV32 = 2.3283064365386963e-10;  // 2^-32
+    constexpr double B32 = 4294967296.0;
+    const double cL = __dsub_rn(__fma_rn(L, INV32, MAGIC4), MAGIC4);
+    L = __fma_rn(cL, -B32, L);
+    H = __dadd_rn(H, cL);
+    const double cH = __dsub_rn(__fma_rn(H, INV32, MAGIC4), MAGIC4);   // cH * 2^64 = cH * (2^32 - 1)
+    H = __fma_rn(cH, -(B32 - 1.0), H);
+    L = __dsub_rn(L, cH);
+}
+__device__ __forceinline__ void normalize_limbs12(double& L, double& H) {
+    constexpr double MAGIC = 6755399441055744.0;              // 1.5 * 2^52: adding it rounds to an integer
+    constexpr double C12 = 1.0 / (12.0 * 4294967296.0);        // any integer k near L / (12 * 2^32) is a valid carry count
+    constexpr double B32 = 4294967296.0;
+    const double kL = __dsub_rn(__fma_rn(L, C12, MAGIC), MAGIC);
+    L = __fma_rn(kL, -12.0 * B32, L);
+    H = __fma_rn(kL, 12.0, H);
+    const double kH = __dsub_rn(__fma_rn(H, C12, MAGIC), MAGIC);
+    H = __fma_rn(kH, -12.0 * (B32 - 1.0), H);
+    L = __fma_rn(kH, -12.0, L);
+}
+
+__device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
+    Freq5 FL, FH;
+    {
+        double l[WIDTH], h[WIDTH];
+        l[0] = h[0] = 0.0;
+#pragma unroll
+        for (int i = 1; i < WIDTH; i++) {
+            l[i] = limb_to_double((uint32_t)s[i]);
+            h[i] = limb_to_double((uint32_t)(s[i] >> 32));
+        }
+        freq5_forward(l, FL);
+        freq5_forward(h, FH);
+    }
+    uint64_t x0 = s[0];
+    double eL = 0.0, eH = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < N_PARTIAL; r++) {
+        double yL, yH;
+        sbox7_limbs(x0, yL, yH);
+        freq5_round(FL, yL, eL);
+        freq5_round(FH, yH, eH);
+        if (r & 1) {   // rounds 5, 7, .., 25
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                normalize_limbs4(FL.a[i], FH.a[i]);
+                normalize_limbs4(FL.b[i], FH.b[i]);
+            }
+            normalize_limbs12(FL.p[0], FH.p[0]);
+            normalize_limbs12(FL.p[1], FH.p[1]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) normalize_limbs12(FL.q[i], FH.q[i]);
+        }
+        eL = freq5_lane0(FL);
+        eH = freq5_lane0(FH);
+        x0 = recombine(__dadd_rn(eL, POSEIDON_PARTIAL4_Q[r][0]), __dadd_rn(eH, POSEIDON_PARTIAL4_Q[r][1]));
+    }
+    s[0] = x0;
+    // back to the time domain: m_j/2 from the CRT back-map, then s_i = (a_i + b_i)/4 + m_i/2, s_{i+6} = (a_i + b_i)/4 - m_i/2,
+    // s_{i+3}, s_{i+9} with a_i - b_i and m_{i+3}
+    double l[WIDTH], h[WIDTH];
+    {
+        const Freq5* F[2] = {&FL, &FH};
+        double* out[2] = {l, h};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const Freq5& f = *F[k];
+            double mh[6];
+            mh[0] = third_half(__fma_rn(f.q[0], 2.0, __dadd_rn(f.p[0], f.q[2])));
+            mh[1] = third_half(__fma_rn(f.q[1], 2.0, __dadd_rn(f.p[1], f.q[3])));
+            mh[2] = third_half(__fma_rn(f.q[2], 2.0, __dsub_rn(f.q[0], f.p[0])));
+            mh[3] = third_half(__fma_rn(f.q[3], 2.0, __dsub_rn(f.q[1], f.p[1])));
+            mh[4] = third_half(__dadd_rn(__dsub_rn(f.p[0], f.q[0]), f.q[2]));
+            mh[5] = third_half(__dadd_rn(__dsub_rn(f.p[1], f.q[1]), f.q[3]));
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double tp = __dadd_rn(f.a[i], f.b[i]), tm = __dsub_rn(f.a[i], f.b[i]);
+                out[k][i] = __fma_rn(tp, 0.25, mh[i]);
+                out[k][i + 6] = __fma_rn(tp, 0.25, -mh[i]);
+                out[k][i + 3] = __fma_rn(tm, 0.25, mh[i + 3]);
+                out[k][i + 9] = __fma_rn(tm, 0.25, -mh[i + 3]);
+            }
+        }
     }
 #pragma unroll
     for (int i = 1; i < WIDTH; i++)

@@ -424,6 +424,174 @@ def permute_v4(state, rc, stats=None):
     return s
 
 
+# ======================================================================================================================
+# v5: the negacyclic-6 part is split once more, x^6+1 = (x^2+1)(x^4-x^2+1): p = m mod (x^2+1), q = m mod (x^4-x^2+1)
+# ======================================================================================================================
+# m' = m*G mod (x^6+1) with G = 2*[2,-4,16,1,-1,-1] becomes p' = p*(-30-12x) mod (x^2+1) (4 products) and
+# q' = q*(6-6x+30x^2) mod (x^4-x^2+1) (13 products) instead of 36.  The CRT back-map divides by 3
+# (3 m0 = p0 + 2 q0 + q2, ...), done exactly by rounding t/6 to the nearest half-integer; carries of p and q are
+# multiples of 12 so that every limb stays divisible.
+from fractions import Fraction as _Fr
+C_INV_12_2P32 = 1.0 / (12.0 * 4294967296.0)      # the fp64 constant the CUDA code multiplies by
+C_INV_6 = 1.0 / 6.0
+
+
+def m_to_pq(m):
+    return [m[0] - m[2] + m[4], m[1] - m[3] + m[5]], [m[0] - m[4], m[1] - m[5], m[2] + m[4], m[3] + m[5]]
+
+
+def rint_half_div6(t):
+    """what (t*fl(1/6) + 1.5*2^51) - 1.5*2^51 computes: t/6 rounded to a multiple of 1/2, returned as 2*value (an int).
+    Exact whenever t is a multiple of 3 and |t| < 2^52 (error of the product < 1/4)."""
+    x = _Fr(t.v) * _Fr(C_INV_6) * 2
+    k = round(x)                                   # nearest integer of 2*t/6 (ties cannot occur for multiples of 3)
+    assert t.v % 3 == 0 and k == t.v // 3 and abs(t.m) < (1 << 52)
+    return BV(k, (t.m + 2) // 3)                   # = m0 (so that m0/2 is the half-integer)
+
+
+def pq_lane0_m0(pp, q):
+    t = q[0].fma(2, pp[0] + q[2])                  # 3*m0
+    return rint_half_div6(t)
+
+
+def freq5_round(a, b, pp, q, y, e):
+    d = y - e
+    a0 = a[0] + d; b0 = b[0] + d; p0 = pp[0] + d; q0 = q[0] + d
+    t1 = (a[1] + a[2]).scale(64)
+    na = [y.fma(8, a0.fma(64, a[2].fma(64, t1))), a0.fma(128, t1), a0.fma(64, a[1].fma(64, t1))]
+    nb = [y.fma(8, b0.fma(-4, b[2].fma(32, b[1].scale(-8)))),
+          b0.fma(-32, b[1].fma(-4, b[2].scale(-8))),
+          b0.fma(8, b[1].fma(-32, b[2].scale(-4)))]
+    np_ = [y.fma(8, p0.fma(-30, pp[1].scale(12))), p0.fma(-12, pp[1].scale(-30))]
+    nq = [y.fma(8, q0.fma(6, q[2].fma(-30, q[3].scale(6)))),
+          q0.fma(-6, q[1].fma(6, q[3].scale(-30))),
+          q0.fma(30, q[1].fma(-6, q[2].fma(36, q[3].scale(-6)))),
+          q[1].fma(30, q[2].fma(-6, q[3].scale(36)))]
+    return na, nb, np_, nq
+
+
+def freq5_lane0(a, b, pp, q):
+    m0 = pq_lane0_m0(pp, q)
+    e4 = a[0].v + b[0].v + 2 * m0.v
+    assert e4 % 4 == 0
+    return BV(e4 // 4, (a[0].m + b[0].m + 2 * m0.m + 3) // 4)
+
+
+def normalize_k(L, H, mult):
+    """carries are multiples of `mult` (4: magic rounding at 2^54; 12: k = rint(L*fl(2^-32/12)), carry 12k)"""
+    def carry(x):
+        if mult == 4:
+            return rint4_div32(x.v), (x.m >> 32) + 2
+        k = round(_Fr(x.v) * _Fr(C_INV_12_2P32))
+        return 12 * k, (x.m >> 32) + 12
+    half = (mult // 2) << 32
+    cL, cLm = carry(L)
+    L1 = BV(L.v - (cL << 32), half + (1 << 12)); H1 = BV(H.v + cL, H.m + cLm)
+    cH, cHm = carry(H1)
+    H2 = BV(H1.v - (cH << 32) + cH, half + (1 << 12) + cHm)
+    L2 = BV(L1.v - cH, L1.m + cHm)
+    assert (L2.v + (H2.v << 32) - L.v - (H.v << 32)) % P == 0
+    return L2, H2
+
+
+def permute_v5(state, rc, stats=None):
+    """Mirror of csrc/poseidon.cuh · permute (v5) on exact integers with proven magnitude bounds."""
+    lane0_c, tail_c = partial_constants(rc)
+    s = [(state[i] + rc[i]) % P for i in range(12)]
+
+    def full_round(s, r):
+        lo, hi = zip(*[sbox_limbs(x) for x in s])
+        lanes = [rc[12 * (r + 1) + i] if r < 29 else 0 for i in range(12)]
+        limbs = [rc_limbs(c) for c in lanes]
+        out = []
+        for limb, ins, off in ((0, list(lo), OFF_LO), (1, list(hi), OFF_HI)):
+            k = [int(x) for x in fold_constants([l[limb] + BIAS + off for l in limbs])]
+            o = mds_limb_checked(ins, k)
+            assert all(BIAS <= x < 2 * BIAS for x in o)
+            out.append([x - BIAS for x in o])
+        return [(out[0][i] + (out[1][i] << 32)) % P for i in range(12)]
+
+    for r in range(0, 4):
+        s = full_round(s, r)
+    x0 = s[0]
+    zero = BV(0, 0)
+    fr = []
+    for limb in (0, 1):
+        lanes = [zero] + [BV((v >> (32 * limb)) & 0xFFFFFFFF, (1 << 32) - 1) for v in s[1:]]
+        a, b, m = freq_forward(lanes)
+        pp, q = m_to_pq(m)
+        fr.append([a, b, pp, q])
+    e = [zero, zero]
+    for r in range(4, 26):
+        y = sbox_limbs_bv(x0)
+        for limb in (0, 1):
+            fr[limb] = list(freq5_round(*fr[limb], y[limb], e[limb]))
+        if stats is not None:
+            stats["max_unnorm"] = max(stats.get("max_unnorm", 0), max(x.m for l in fr for part in l for x in part))
+        if r & 1:
+            for part, mult in ((0, 4), (1, 4), (2, 12), (3, 12)):
+                for i in range(len(fr[0][part])):
+                    fr[0][part][i], fr[1][part][i] = normalize_k(fr[0][part][i], fr[1][part][i], mult)
+        xs = []
+        for limb in (0, 1):
+            e[limb] = freq5_lane0(*fr[limb])
+            c = rc_limbs(lane0_c[r + 1])[limb]
+            X = e[limb] + bv_const(c + BIAS + (OFF4_LO, OFF4_HI)[limb])
+            assert BIAS <= X.v < 2 * BIAS and e[limb].m < (1 << 51), "lane 0 read-out window"
+            xs.append(X.v - BIAS)
+        x0 = (xs[0] + (xs[1] << 32)) % P
+    out = [x0]
+    lanes = [[None] * 12, [None] * 12]
+    for limb in (0, 1):
+        a, b, pp, q = fr[limb]
+        # 3*m_j from the CRT back-map, then m_j = rint_half(t/6)*2
+        t3 = [q[0].fma(2, pp[0] + q[2]), q[1].fma(2, pp[1] + q[3]), q[2].fma(2, q[0] - pp[0]),
+              q[3].fma(2, q[1] - pp[1]), (pp[0] - q[0]) + q[2], (pp[1] - q[1]) + q[3]]
+        m = [rint_half_div6(t) for t in t3]
+        for i in range(3):
+            tp, tm = a[i] + b[i], a[i] - b[i]
+            for (t, j) in ((tp, i), (tm, i + 3)):
+                for sign, lane in ((1, j), (-1, j + 6)):
+                    v4 = t.v + 2 * sign * m[j].v
+                    assert v4 % 4 == 0
+                    lanes[limb][lane] = BV(v4 // 4, (t.m + 2 * m[j].m + 3) // 4)
+    for i in range(1, 12):
+        cl, ch = rc_limbs(tail_c[i - 1])
+        al = lanes[0][i] + bv_const(cl + OFF4_LO + BIAS); ah = lanes[1][i] + bv_const(ch + OFF4_HI + BIAS)
+        assert BIAS <= al.v < 2 * BIAS and BIAS <= ah.v < 2 * BIAS
+        assert lanes[0][i].m < (1 << 51) and lanes[1][i].m < (1 << 51)
+        out.append(((al.v - BIAS) + ((ah.v - BIAS) << 32)) % P)
+    s = out
+    for r in range(26, 30):
+        s = full_round(s, r)
+    return s
+
+
+def selftest_v5():
+    import os, sys, random
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from gen_poseidon_constants import constants
+    rc = constants()
+    rnd = random.Random(9)
+    # one round of the split form against the time-domain layer (no normalisation involved)
+    for _ in range(50):
+        sv = [rnd.randrange(-(1 << 33), 1 << 33) for _ in range(12)]
+        yv = rnd.randrange(-(1 << 33), 1 << 33)
+        a, b, m = freq_forward([BV(v, 1 << 33) for v in sv])
+        pp, q = m_to_pq(m)
+        na, nb, np_, nq = freq5_round(a, b, pp, q, BV(yv, 1 << 33), BV(sv[0], 1 << 33))
+        want = mds_direct([yv] + sv[1:])
+        wa, wb, wm = freq_forward([BV(v, abs(v) + 1) for v in want])
+        wp, wq = m_to_pq(wm)
+        assert [x.v for x in na + nb + np_ + nq] == [x.v for x in wa + wb + wp + wq]
+    stats = {}
+    tests = [[0] * 12, list(range(12)), [P - 1] * 12] + [[rnd.randrange(P) for _ in range(60)]]
+    tests = tests[:3] + [[rnd.randrange(P) for _ in range(12)] for _ in range(60)]
+    for st in tests:
+        assert permute_v5(st, rc, stats) == permute_naive(st, rc)
+    print("permute_v5 model ok; proven bound on resident components = 2^%.2f" % (stats["max_unnorm"].bit_length()))
+
+
 def selftest_v4():
     import os, sys, random
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -439,3 +607,4 @@ def selftest_v4():
 
 if __name__ == "__main__":
     selftest_v4()
+    selftest_v5()

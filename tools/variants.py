@@ -9,18 +9,12 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "plonky2.5_b200", "variants")
 VARIANTS = {
-    "base_v3":        ["-DPOSEIDON_PARTIAL_V3", "-DPOSEIDON_SBOX_FORM=0x0", "-DGL_MUL_NEW=0"],
-    "v4_form0":       ["-DPOSEIDON_SBOX_FORM=0x0", "-DGL_MUL_NEW=0"],
-    "v4_formF":       ["-DPOSEIDON_SBOX_FORM=0xF", "-DGL_MUL_NEW=1"],
-    "v4_formE":       ["-DPOSEIDON_SBOX_FORM=0xE", "-DGL_MUL_NEW=1"],
-    "v4_formC":       ["-DPOSEIDON_SBOX_FORM=0xC", "-DGL_MUL_NEW=1"],
-    "v4_formD":       ["-DPOSEIDON_SBOX_FORM=0xD", "-DGL_MUL_NEW=1"],
-    "v4_form8":       ["-DPOSEIDON_SBOX_FORM=0x8", "-DGL_MUL_NEW=1"],
-    "v4_form4":       ["-DPOSEIDON_SBOX_FORM=0x4", "-DGL_MUL_NEW=1"],
-    "v3_formE":       ["-DPOSEIDON_PARTIAL_V3", "-DPOSEIDON_SBOX_FORM=0xE", "-DGL_MUL_NEW=1"],
-    "v4_form0_r80":   ["-DPOSEIDON_SBOX_FORM=0x0", "-DGL_MUL_NEW=0", "-maxrregcount=80"],
-    "v4_formE_r80":   ["-DPOSEIDON_SBOX_FORM=0xE", "-DGL_MUL_NEW=1", "-maxrregcount=80"],
-    "v4_form8_r80":   ["-DPOSEIDON_SBOX_FORM=0x8", "-DGL_MUL_NEW=1", "-maxrregcount=80"],
+    "v5":             [],
+    "v5_fp64handoff": ["-DPOSEIDON_HANDOFF_FP64"],
+    "v4":             ["-DPOSEIDON_PARTIAL_V4"],
+    "v4_fp64handoff": ["-DPOSEIDON_PARTIAL_V4", "-DPOSEIDON_HANDOFF_FP64"],
+    "v5_form0":       ["-DPOSEIDON_SBOX_FORM=0x0"],
+    "v5_formE":       ["-DPOSEIDON_SBOX_FORM=0xE"],
 }
 
 
