@@ -290,7 +290,10 @@ void merkle_build(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32
                   uint32_t* tree_launches, cudaEvent_t after_leaves) {
     uint32_t log_leaves = log2_exact(n_leaves);
     uint32_t log_sub = log_leaves - cap_height;
-    constexpr int LB = 128;
+#ifndef LEAF_BLOCK
+#define LEAF_BLOCK 128
+#endif
+    constexpr int LB = LEAF_BLOCK;
     merkle::leaf_hash_kernel<LB><<<(uint32_t)((n_leaves + LB - 1) / LB), LB, 0, c->stream>>>(
         d_leaves, pitch, leaf_len, n_leaves, log_sub, d_digests, d_cap);
     CUDA_CHECK(cudaGetLastError());

@@ -24,8 +24,11 @@ __device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[
 }
 
 // One thread per leaf: hash_or_noop(row) with the overwrite-mode rate-8 sponge.
+#ifndef LEAF_MIN_BLOCKS
+#define LEAF_MIN_BLOCKS 6   // 80 registers: measured 43.2 ms vs 44.0 ms at 94-106 registers (2^22 x 135 leaves)
+#endif
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, LEAF_MIN_BLOCKS)
 leaf_hash_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t leaf_len, uint64_t n_leaves,
                  uint32_t log_sub, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap) {
     uint64_t leaf = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
