@@ -308,6 +308,9 @@ def main():
                       if world == 1 else "pinned host shard -> device, sharded commit, cap to host"}
 
     if world > 1:
+        if os.environ.get("GL_BENCH_PHASES"):
+            print(f"rank {rank} host-side phase ms of the last commit: " + json.dumps({k: round(v, 3) for k, v in state.phase_ms.items()}),
+                  file=sys.stderr, flush=True)
         state.close()
     if rank != 0:
         if world > 1:
@@ -352,7 +355,7 @@ def main():
         except (OSError, KeyError):
             pass
 
-    cpu = None if a.no_cpu_baseline else cpu_baseline(a)
+    cpu = None if (a.no_cpu_baseline or world > 1) else cpu_baseline(a)   # rank 0 at N=1 only
 
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",

@@ -40,7 +40,7 @@ enum {
     GL_ERR_UNSUPPORTED = -5  /* shape outside what the kernels support (e.g. log_n + rate_bits > 32)             */
 };
 
-#define GL_ABI_VERSION 1
+#define GL_ABI_VERSION 2
 int gl_abi_version(void);
 const char* gl_strerror(int code);
 
@@ -134,10 +134,13 @@ int gl_dev_lde(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_
  * NTT pass of every coset stores each leaf-row segment directly into the leaf buffer of the rank that owns that row:
  * global leaf row i lives in peer_leaves[i / (R/n_peers)] at row i % (R/n_peers), columns [col_off, col_off+n_cols) of
  * a [R/n_peers][leaf_pitch] matrix.  peer_leaves: HOST array of n_peers device pointers (own buffer + buffers mapped
- * with gl_dev_ipc_open).  The caller synchronises the ranks (barrier) before hashing.                                */
+ * with gl_dev_ipc_open).  The caller synchronises the ranks (barrier) before hashing.  The 2^rate_bits cosets are
+ * processed in the order first_coset, first_coset+1, ... (mod 2^rate_bits): ranks that start at different cosets store
+ * to different owners at any one time instead of all converging on one GPU's NVLink ingress.                        */
 int gl_dev_lde_scatter(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,
                        uint32_t rate_bits, int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers,
-                       uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch);
+                       uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch,
+                       uint32_t first_coset);
 /* CUDA IPC plumbing for the above: export a device buffer (64-byte handle) / map a peer's / unmap / free */
 int gl_dev_ipc_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]);
 int gl_dev_ipc_open(gl_ctx* ctx, const uint8_t handle[64], uint64_t** out_ptr);

@@ -340,7 +340,8 @@ void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream))
 // host->device copies in gl_commit).  col0 must be a multiple of 8.
 void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t col0, uint32_t n_cols, uint32_t width,
                  uint32_t log_n, uint32_t rate_bits, int is_coeffs, uint64_t* d_vals, uint64_t* d_coeffs, uint32_t coeff_pitch,
-                 uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events, const ntt::Scatter* scatter = nullptr) {
+                 uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events, const ntt::Scatter* scatter = nullptr,
+                 uint32_t first_coset = 0) {
     const uint64_t N = 1ULL << log_n;
     const uint32_t cols_padded = round_up(n_cols, G);
     dim3 tb(32, 8);
@@ -363,7 +364,8 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
     }
     if (split_events) record(c, GL_STAGE_LDE);
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
-    for (uint32_t s = 0; s < (1u << rate_bits); s++) {
+    for (uint32_t k = 0; k < (1u << rate_bits); k++) {
+        const uint32_t s = (k + first_coset) & ((1u << rate_bits) - 1);
         if (scatter) {   // d_rows is an [N][row_pitch] scratch reused by every coset (stream order)
             ntt::Scatter sc = *scatter;
             sc.row0 = (uint64_t)h_bitrev(s, rate_bits) * N;
@@ -593,7 +595,7 @@ int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
 
 int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
                        int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
-                       uint64_t* d_out_coeffs, uint32_t coeff_pitch) {
+                       uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset) {
     GL_API_BEGIN(c)
     check_shape(n_cols, log_n, rate_bits, 0);
     if (!d_cols || !peer_leaves || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
@@ -620,7 +622,7 @@ int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, u
     for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
     record(c, GL_STAGE_TRANSPOSE);
     lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch,
-                c->scratch.p, coeff_pitch, G, true, true, &sc);
+                c->scratch.p, coeff_pitch, G, true, true, &sc, first_coset);
     record(c, GL_STAGE_LEAF_HASH);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})

@@ -37,8 +37,19 @@ class ShardPlan:
         self.n_rows = 1 << (log_n + rate_bits)               # R
         self.rows_per_rank = self.n_rows // world
         self.local_cap_height = cap_height - (world.bit_length() - 1)
-        base, rem = divmod(n_cols, world)
-        self.col_counts = [base + (1 if g < rem else 0) for g in range(world)]
+        # Columns are dealt in groups of 4 (32 bytes of a leaf row) so that every rank's column offset is sector aligned: the
+        # fused exchange stores whole 32-byte sectors into the owners' leaf buffers (a rank starting at an odd multiple of
+        # 16 bytes was measured 1.5x slower: two partial sectors per segment over NVLink).  The NTTs work on 4-column
+        # groups anyway, so the padded work per rank is the same as for an even per-column split.
+        n_groups = (n_cols + 3) // 4
+        if n_groups >= world:
+            base, rem = divmod(n_groups, world)
+            groups = [base + (1 if g < rem else 0) for g in range(world)]
+            self.col_counts = [4 * k for k in groups]
+            self.col_counts[-1] -= 4 * n_groups - n_cols          # the last group may be partial
+        else:                                                     # very narrow batches: plain even split
+            base, rem = divmod(n_cols, world)
+            self.col_counts = [base + (1 if g < rem else 0) for g in range(world)]
         self.col_offsets = [sum(self.col_counts[:g]) for g in range(world)]
         # device pitch of a rank's LDE output: multiple of 4 words (see gl_dev_lde), of 8 when that wastes < 4 columns
         self.pitches = [_round_up(c, 8) if _round_up(c, 8) - c < 4 else _round_up(c, 4) for c in self.col_counts]
@@ -95,7 +106,17 @@ class ShardedCommit:
         self.cap_dev = torch.empty(4 << p.local_cap_height, dtype=i64, device=dev)
         self.cap_all = torch.empty(4 << p.cap_height, dtype=i64, device=dev)
         self.exchange_ms = 0.0
+        self.phase_ms = {}
+        self._merkle_call_ms = 0.0
         self._peer_ptrs = None
+        self._stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        # leaf row i = LDE point bitrev(i): the rows of rank q are those of cosets bitrev_r(j), j in [q*2^r/G, (q+1)*2^r/G)
+        # (G <= 2^r), so starting rank q at coset bitrev_r(q*2^r/G) makes every rank store into its OWN buffer first and into
+        # a different owner than any other rank at every later step
+        n_cosets = 1 << p.rate_bits
+        j = (rank * n_cosets // p.world) % n_cosets
+        self._first_coset = int(format(j, "0%db" % p.rate_bits)[::-1], 2) if p.rate_bits else 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         if exchange == "p2p" and self._init_p2p(dev):
             return
         self.exchange = "nccl"      # requested, or the ranks cannot map each other's memory (all ranks agree on this)
@@ -165,13 +186,26 @@ class ShardedCommit:
         n = 1 << p.log_n
         ncg = p.col_counts[self.rank]
         assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
+        import time
+        t0 = time.perf_counter()
         if self.exchange == "p2p":
-            # everyone must be done READING its leaf buffer (previous commit's hashing) before anyone writes into it again
-            self.dist.barrier()
+            # Nobody may write into a leaf buffer its owner is still hashing: the previous commit ended with the cap
+            # all-gather, which no rank enters before its own hashing is done, and every rank read its result — so all
+            # leaf buffers are free here without a further barrier (the first commit follows _init_p2p's barrier).
             self._check(lib.gl_dev_lde_scatter(h, d_cols.data_ptr(), n, ncg, p.log_n, p.rate_bits, 0, self._peer_ptrs, p.world,
-                                               p.leaf_pitch, p.col_offsets[self.rank], self.coeffs.data_ptr(), p.pitches[self.rank]))
-            self.dist.barrier()      # all peers' stores have landed (each rank synchronised its stream before the barrier)
-            return self._hash()
+                                               p.leaf_pitch, p.col_offsets[self.rank], self.coeffs.data_ptr(), p.pitches[self.rank],
+                                               self._first_coset))
+            # device-side barrier on the library's stream: a 1-element all-reduce completes only after every rank's scatter
+            # kernels (stream order), and the hashing kernels queue behind it — no host round trip
+            t1 = time.perf_counter()
+            with torch.cuda.stream(self._stream):
+                self.dist.all_reduce(self._flag)
+            t2 = time.perf_counter()
+            out = self._hash()
+            t3 = time.perf_counter()
+            self.phase_ms = {"lde_scatter_call": (t1 - t0) * 1e3, "barrier_enqueue": (t2 - t1) * 1e3, "hash_and_cap_gather": (t3 - t2) * 1e3,
+                             "merkle_call": self._merkle_call_ms}
+            return out
         self._check(lib.gl_dev_lde(h, d_cols.data_ptr(), n, ncg, p.log_n, p.rate_bits, 0, self.rows.data_ptr(), p.pitches[self.rank],
                                    self.coeffs.data_ptr()))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -189,8 +223,12 @@ class ShardedCommit:
 
     def _hash(self) -> np.ndarray:
         p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
+        import time
+        t0 = time.perf_counter()
         self._check(lib.gl_dev_merkle(h, self.leaves_ptr, p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
                                       self.digests.data_ptr(), self.cap_local.ctypes.data))
-        self.cap_dev.copy_(torch.from_numpy(self.cap_local.view(np.int64)))
-        self.dist.all_gather_into_tensor(self.cap_all, self.cap_dev)
-        return self.cap_all.cpu().numpy().view(np.uint64)
+        self._merkle_call_ms = (time.perf_counter() - t0) * 1e3
+        with torch.cuda.stream(self._stream):
+            self.cap_dev.copy_(torch.from_numpy(self.cap_local.view(np.int64)))
+            self.dist.all_gather_into_tensor(self.cap_all, self.cap_dev)
+            return self.cap_all.cpu().numpy().view(np.uint64)

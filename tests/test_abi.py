@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gl_commit.h but not exported"
     # and the Python binding covers exactly the header
     assert sorted(_lib.SIGNATURES) == declared
-    assert _lib.load().gl_abi_version() == 1
+    assert _lib.load().gl_abi_version() == 2
 
 
 def test_sass_is_sm_100a_only():

@@ -15,7 +15,10 @@ def test_plan_partitions_cover_everything():
         p = ShardPlan(cols, log_n, r, h, world)
         assert sum(p.col_counts) == cols and p.col_offsets[0] == 0
         assert all(p.col_range(k)[1] == p.col_range(k + 1)[0] for k in range(world - 1))
-        assert max(p.col_counts) - min(p.col_counts) <= 1
+        padded = [(c + 3) // 4 * 4 for c in p.col_counts]
+        assert min(p.col_counts) >= 1 and max(padded) - min(padded) <= 4          # balanced in units of the NTT's 4-column groups
+        if (cols + 3) // 4 >= world:
+            assert all(o % 4 == 0 for o in p.col_offsets)                         # sector-aligned column offsets
         assert p.rows_per_rank * world == 1 << (log_n + r)
         assert (1 << p.local_cap_height) * world == 1 << h
         assert all(pt % 4 == 0 and pt >= c and pt - c < 4 for pt, c in zip(p.pitches, p.col_counts))
