@@ -215,6 +215,11 @@ const std::vector<CosetTable>& get_lde_tables(gl_ctx* c, uint32_t log_n, uint32_
     return ref;
 }
 
+template <int G, int A>
+void launch_pass_a(gl_ctx* c, const ntt::PassParams& p, uint32_t threads, size_t smem, uint32_t grid) {   // smem <= 44 KB for every (G, a)
+    ntt::ntt_pass_kernel<G, A><<<grid, threads, smem, c->stream>>>(p);
+}
+
 template <int G>
 void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* launches) {
     p.ncg = cols_padded / G;
@@ -223,7 +228,21 @@ void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* l
     size_t smem = ((size_t)(T + (T >> 3)) * G + (T - (T >> 3))) * 8;   // padded tile + 7T/8 twiddles
     uint64_t grid = (uint64_t)p.ncg << (p.log_n - p.a);
     if (grid >= (1ULL << 31)) GL_THROW(GL_ERR_UNSUPPORTED, "NTT grid too large");
-    ntt::ntt_pass_kernel<G><<<(uint32_t)grid, threads, smem, c->stream>>>(p);
+    if (G == 2) {
+        launch_pass_a<G, 0>(c, p, threads, smem, (uint32_t)grid);      // FRI matrices: generic pass size
+    } else {
+        switch (p.a) {                                                  // pass size as a compile-time constant
+            case 3: launch_pass_a<G, 3>(c, p, threads, smem, (uint32_t)grid); break;
+            case 4: launch_pass_a<G, 4>(c, p, threads, smem, (uint32_t)grid); break;
+            case 5: launch_pass_a<G, 5>(c, p, threads, smem, (uint32_t)grid); break;
+            case 6: launch_pass_a<G, 6>(c, p, threads, smem, (uint32_t)grid); break;
+            case 7: launch_pass_a<G, 7>(c, p, threads, smem, (uint32_t)grid); break;
+            case 8: launch_pass_a<G, 8>(c, p, threads, smem, (uint32_t)grid); break;
+            case 9: launch_pass_a<G, 9>(c, p, threads, smem, (uint32_t)grid); break;
+            case 10: launch_pass_a<G, 10>(c, p, threads, smem, (uint32_t)grid); break;
+            default: GL_THROW(GL_ERR_INVALID, "bad pass size %u", p.a);
+        }
+    }
     CUDA_CHECK(cudaGetLastError());
     if (launches) (*launches)++;
 }

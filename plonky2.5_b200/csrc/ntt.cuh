@@ -104,10 +104,13 @@ __device__ __forceinline__ void radix8_round(uint64_t (&x)[8], const uint64_t* _
     }
 }
 
-template <int G>
-__global__ void ntt_pass_kernel(const PassParams p) {
+// A > 0: the pass size is a compile-time constant (round shifts, tile addressing and the round structure fold away);
+// A == 0: generic (runtime p.a) — used for the 2-column FRI matrices.
+template <int G, int A>
+__global__ void __launch_bounds__(A ? (1 << A) * G / 8 : 1024, A ? ((1536 * 8 / ((1 << A) * G)) > 16 ? 16 : (1536 * 8 / ((1 << A) * G)) ? (1536 * 8 / ((1 << A) * G)) : 1) : 1)
+ntt_pass_kernel(const PassParams p) {   // >= 48 resident warps per SM where the shape allows it
     extern __shared__ uint64_t sm[];
-    const uint32_t a = p.a, T = 1u << a;
+    const uint32_t a = A ? A : p.a, T = 1u << a;
     uint64_t* tile = sm;
     uint64_t* Wl = sm + (size_t)(T + (T >> 3)) * G;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;   // nthr = T*G/8
@@ -136,19 +139,42 @@ __global__ void ntt_pass_kernel(const PassParams p) {
         }
     }
     __syncthreads();   // Wl ready
-    uint32_t remaining = a;
-    while (true) {
-        const uint32_t nst = remaining >= 3 ? 3 : remaining;
-        radix8_round(x, Wl, a, sh, q & ((1u << sh) - 1), nst);
-        remaining -= nst;
-        if (remaining == 0) break;
+    if (A) {
+        // compile-time round structure: round r does min(3, A - 3r) stages at shift max(A - 3(r+1), 0)
+        constexpr int ROUNDS = (A + 2) / 3;
 #pragma unroll
-        for (int e = 0; e < 8; e++) tile[(size_t)phys_row(ins3(q, sh, e)) * G + c] = x[e];
-        __syncthreads();
-        sh = remaining >= 3 ? remaining - 3 : 0;
+        for (int r = 0; r < ROUNDS; r++) {
+            constexpr int AA = A ? A : 3;
+            const int done = 3 * r, left = AA - done;
+            const uint32_t nst = left >= 3 ? 3 : left;
+            const uint32_t shr = left >= 3 ? left - 3 : 0;
+            if (r > 0) {
+                const uint32_t shp = AA - 3 * r;   // shift of the previous round (>= 0 because r < ROUNDS)
 #pragma unroll
-        for (int e = 0; e < 8; e++) x[e] = tile[(size_t)phys_row(ins3(q, sh, e)) * G + c];
-        __syncthreads();
+                for (int e = 0; e < 8; e++) tile[(size_t)phys_row(ins3(q, shp, e)) * G + c] = x[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = tile[(size_t)phys_row(ins3(q, shr, e)) * G + c];
+                if (r + 1 < ROUNDS) __syncthreads();   // the tile is rewritten by the next exchange
+            }
+            radix8_round(x, Wl, a, shr, q & ((1u << shr) - 1), nst);
+            sh = shr;
+        }
+    } else {
+        uint32_t remaining = a;
+        while (true) {
+            const uint32_t nst = remaining >= 3 ? 3 : remaining;
+            radix8_round(x, Wl, a, sh, q & ((1u << sh) - 1), nst);
+            remaining -= nst;
+            if (remaining == 0) break;
+#pragma unroll
+            for (int e = 0; e < 8; e++) tile[(size_t)phys_row(ins3(q, sh, e)) * G + c] = x[e];
+            __syncthreads();
+            sh = remaining >= 3 ? remaining - 3 : 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = tile[(size_t)phys_row(ins3(q, sh, e)) * G + c];
+            __syncthreads();
+        }
     }
     // sh is the shift of the last round: element e of this thread is tile row l = ins3(q, sh, e)
     const uint32_t N = 1u << p.log_n;

@@ -9,14 +9,7 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "plonky2.5_b200", "variants")
 VARIANTS = {
-    "v5":             [],
-    "v5_mb6":         ["-DLEAF_MIN_BLOCKS=6"],
-    "v5_mb4":         ["-DLEAF_MIN_BLOCKS=4"],
-    "v5_mb3":         ["-DLEAF_MIN_BLOCKS=3"],
-    "v5_b64":         ["-DLEAF_BLOCK=64"],
-    "v5_b64_mb12":    ["-DLEAF_BLOCK=64", "-DLEAF_MIN_BLOCKS=12"],
-    "v5_b256":        ["-DLEAF_BLOCK=256"],
-    "v5_b32":         ["-DLEAF_BLOCK=32"],
+    "default":        [],
 }
 
 
