@@ -109,6 +109,26 @@ int gl_fri_fold(gl_ctx* ctx, gl_handle fri, const uint64_t beta[2]);
 int gl_fri_final_poly(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* out_len);
 int gl_fri_end(gl_ctx* ctx, gl_handle fri);
 
+/* ---- prove_openings, front half  (plonky2 fri/oracle.rs · PolynomialBatch::prove_openings) ----------------------
+ * Builds the polynomial that goes into FRI from the device-resident coefficient matrices of earlier commits:
+ *     final_poly = 0
+ *     for every FriBatchInfo { point, polynomials }:                          (gl_openings_add_batch)
+ *         F        = sum_j alpha^j * f_j                 ReducingFactor::reduce_polys_base (powers restart at alpha^0)
+ *         quotient = (F(X) - F(point)) / (X - point)     divide_by_linear, then coeffs.push(ZERO)
+ *         final_poly = final_poly * alpha^(number of polynomials of this batch) + quotient     shift_poly, +=
+ *     lde_final_poly = final_poly.lde(rate_bits); lde_final_values = lde_final_poly.coset_fft(7)     (gl_openings_lde)
+ * polynomial j of a batch is column columns[j] of the commit behind handle batches[j] (all commits of degree 2^log_n);
+ * alpha, point: extension elements [a0, a1].  gl_openings_lde hands the result to the FRI commit phase as a gl_fri
+ * handle (what gl_fri_begin would build from host arrays) without leaving the device.                                */
+int gl_openings_begin(gl_ctx* ctx, uint32_t log_n, gl_handle* out_openings);
+int gl_openings_add_batch(gl_ctx* ctx, gl_handle openings, const gl_handle* batches, const uint32_t* columns, uint32_t n_polys,
+                          const uint64_t alpha[2], const uint64_t point[2], uint64_t* out_quotient_ext /* N*2 words or NULL */);
+int gl_openings_final_poly(gl_ctx* ctx, gl_handle openings, uint64_t* out_coeffs_ext /* N*2 words */);
+int gl_openings_lde(gl_ctx* ctx, gl_handle openings, uint32_t rate_bits, uint32_t cap_height, gl_handle* out_fri);
+int gl_openings_end(gl_ctx* ctx, gl_handle openings);
+/* read the current coefficients (len extension elements) / bit-reversed values of a gl_fri state (tests, debugging) */
+int gl_fri_read(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* out_values_bitrev_ext, uint64_t* out_len);
+
 /* ---- FRI proof of work: fri_proof_of_work  (plonky2 fri/prover.rs) ---------------------------------------------
  * sponge_state / input_buffer: the caller's Challenger fields (sponge_state, pending input_buffer, n_inputs < 8).
  * Finds the SMALLEST canonical w such that, with the pending inputs written into the state and w in the next input

@@ -525,3 +525,83 @@ def fri_committed_trees(coeffs: List[Ext], values: List[Ext], challenger: Challe
     for c in final:
         challenger.observe_extension_element(c)
     return trees, final
+
+
+# --------------------------------------------------------------------------------------------------------
+# prove_openings, front half (plonky2/src/fri/oracle.rs · PolynomialBatch::prove_openings; util/reducing.rs ·
+# ReducingFactor; field/src/polynomial/division.rs · divide_by_linear) — restated from memory of upstream @ 3de92d9
+# (parity unpinned: no vectors in /root/reference; tests check the algebraic identities instead)
+# --------------------------------------------------------------------------------------------------------
+def ext_pow(a: Ext, e: int) -> Ext:
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ext_mul(r, a)
+        a = ext_mul(a, a)
+        e >>= 1
+    return r
+
+
+class ReducingFactor:
+    def __init__(self, base: Ext):
+        self.base = base
+        self.count = 0
+
+    def reduce_polys_base(self, polys: Sequence[Sequence[int]]) -> List[Ext]:
+        """sum_j base^j * poly_j (powers restart at base^0 on every call; count += number of polynomials)"""
+        n = max((len(p) for p in polys), default=0)
+        acc = [(0, 0)] * n
+        pw = (1, 0)
+        for p in polys:
+            self.count += 1
+            acc = [ext_add(a, ext_scale(pw, c)) for a, c in zip(acc, list(p) + [0] * (n - len(p)))]
+            pw = ext_mul(pw, self.base)
+        return acc
+
+    def shift_poly(self, p: List[Ext]) -> List[Ext]:
+        s = ext_pow(self.base, self.count)
+        self.count = 0
+        return [ext_mul(c, s) for c in p]
+
+
+def ext_divide_by_linear(coeffs: Sequence[Ext], z: Ext) -> List[Ext]:
+    """(p(X) - p(z)) / (X - z): Horner scan from the top coefficient, remainder dropped (one coefficient shorter)."""
+    bs = []
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = ext_add(ext_mul(acc, z), c)
+        bs.append(acc)
+    bs.pop()
+    bs.reverse()
+    return bs
+
+
+def ext_eval_poly_ext(coeffs: Sequence[Ext], x: Ext) -> Ext:
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = ext_add(ext_mul(acc, x), c)
+    return acc
+
+
+def prove_openings_final_poly(batches, oracles, alpha: Ext):
+    """batches: [(point: Ext, [(oracle_index, polynomial_index), ...])]; oracles: lists of coefficient vectors per oracle.
+    Returns (final_poly coefficients [N], the per-batch quotients)."""
+    rf = ReducingFactor(alpha)
+    final: List[Ext] = []
+    quotients = []
+    for point, polys in batches:
+        comp = rf.reduce_polys_base([oracles[o][i] for (o, i) in polys])
+        q = ext_divide_by_linear(comp, point)
+        q.append((0, 0))                                  # pad back to a power of two
+        quotients.append(q)
+        final = rf.shift_poly(final)
+        if not final:
+            final = [(0, 0)] * len(q)
+        final = [ext_add(a, b) for a, b in zip(final, q)]
+    return final, quotients
+
+
+def prove_openings_lde(final_poly: Sequence[Ext], rate_bits: int):
+    """lde_final_poly = final_poly.lde(rate_bits); lde_final_values = lde_final_poly.coset_fft(7)"""
+    lde = list(final_poly) + [(0, 0)] * (len(final_poly) * ((1 << rate_bits) - 1))
+    return lde, ext_coset_fft(lde, MULTIPLICATIVE_GROUP_GENERATOR)

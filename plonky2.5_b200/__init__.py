@@ -7,9 +7,9 @@ repository root) or via importlib.
 """
 from . import _lib  # noqa: F401
 from . import sharded  # noqa: F401
-from .api import (Challenger, Context, FriParams, GlError, MerkleCap, MerkleTree, PolynomialBatch,  # noqa: F401
-                  default_context, fri_committed_trees, fri_proof_of_work)
+from .api import (Challenger, Context, FriBatchInfo, FriParams, FriProofHead, GlError, MerkleCap, MerkleTree,  # noqa: F401
+                  PolynomialBatch, default_context, fri_committed_trees, fri_proof_of_work, prove_openings)
 from .build import build  # noqa: F401
 
-__all__ = ["Challenger", "Context", "FriParams", "GlError", "MerkleCap", "MerkleTree", "PolynomialBatch",
-           "default_context", "fri_committed_trees", "fri_proof_of_work", "build"]
+__all__ = ["Challenger", "Context", "FriBatchInfo", "FriParams", "FriProofHead", "GlError", "MerkleCap", "MerkleTree",
+           "PolynomialBatch", "default_context", "fri_committed_trees", "fri_proof_of_work", "prove_openings", "build"]

@@ -45,6 +45,12 @@ SIGNATURES = {
     "gl_fri_fold": (c_int, [c_void_p, c_uint64, c_void_p]),
     "gl_fri_final_poly": (c_int, [c_void_p, c_uint64, c_void_p, POINTER(c_uint64)]),
     "gl_fri_end": (c_int, [c_void_p, c_uint64]),
+    "gl_openings_begin": (c_int, [c_void_p, c_uint32, POINTER(c_uint64)]),
+    "gl_openings_add_batch": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "gl_openings_final_poly": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "gl_openings_lde": (c_int, [c_void_p, c_uint64, c_uint32, c_uint32, POINTER(c_uint64)]),
+    "gl_openings_end": (c_int, [c_void_p, c_uint64]),
+    "gl_fri_read": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, POINTER(c_uint64)]),
     "gl_fri_pow": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, POINTER(c_uint64)]),
     "gl_poseidon_permute": (c_int, [c_void_p, c_void_p, c_uint64]),
     "gl_dev_commit": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_int, c_void_p,

@@ -341,6 +341,28 @@ class FriParams:
         self.reduction_arity_bits = list(reduction_arity_bits)
 
 
+def _fri_commit_phase(ctx: Context, fh: int, challenger, fri_params: FriParams):
+    """the per-layer loop of fri_committed_trees on a device-resident FRI state (gl_fri handle)"""
+    lib = ctx.lib
+    trees = []
+    for arity_bits in fri_params.reduction_arity_bits:
+        cap = np.zeros(4 << fri_params.cap_height, dtype=np.uint64)
+        th = c_uint64()
+        _check(ctx, lib.gl_fri_commit_layer(ctx.handle, fh, arity_bits, None, None, _ptr(cap), byref(th)))
+        tree = MerkleTree(ctx, th.value, cap)
+        challenger.observe_cap(tree.cap.flatten())
+        trees.append(tree)
+        beta = challenger.get_extension_challenge()
+        b = np.array([int(beta[0]), int(beta[1])], dtype=np.uint64)
+        _check(ctx, lib.gl_fri_fold(ctx.handle, fh, _ptr(b)))
+    n = c_uint64()
+    _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh, None, byref(n)))
+    final = np.zeros((n.value, 2), dtype=np.uint64)
+    _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh, _ptr(final), byref(n)))
+    challenger.observe_extension_elements(final)
+    return trees, final
+
+
 def fri_committed_trees(polynomial_coeffs, polynomial_values, challenger, fri_params: FriParams,
                         ctx: Optional[Context] = None):
     """plonky2 fri/prover.rs · fri_committed_trees.
@@ -354,27 +376,78 @@ def fri_committed_trees(polynomial_coeffs, polynomial_values, challenger, fri_pa
     va = np.ascontiguousarray(polynomial_values, dtype=np.uint64).reshape(-1, 2)
     if co.shape != va.shape:
         raise ValueError("coeffs and values must have the same length")
-    lib = ctx.lib
     fh = c_uint64()
-    _check(ctx, lib.gl_fri_begin(ctx.handle, _ptr(co), _ptr(va), co.shape[0], fri_params.rate_bits, fri_params.cap_height,
-                                 byref(fh)))
-    trees = []
+    _check(ctx, ctx.lib.gl_fri_begin(ctx.handle, _ptr(co), _ptr(va), co.shape[0], fri_params.rate_bits, fri_params.cap_height,
+                                     byref(fh)))
     try:
-        for arity_bits in fri_params.reduction_arity_bits:
-            cap = np.zeros(4 << fri_params.cap_height, dtype=np.uint64)
-            th = c_uint64()
-            _check(ctx, lib.gl_fri_commit_layer(ctx.handle, fh.value, arity_bits, None, None, _ptr(cap), byref(th)))
-            tree = MerkleTree(ctx, th.value, cap)
-            challenger.observe_cap(tree.cap.flatten())
-            trees.append(tree)
-            beta = challenger.get_extension_challenge()
-            b = np.array([int(beta[0]), int(beta[1])], dtype=np.uint64)
-            _check(ctx, lib.gl_fri_fold(ctx.handle, fh.value, _ptr(b)))
+        return _fri_commit_phase(ctx, fh.value, challenger, fri_params)
+    finally:
+        ctx.lib.gl_fri_end(ctx.handle, fh.value)
+
+
+class FriBatchInfo:
+    """plonky2 fri/structure.rs · FriBatchInfo { point, polynomials: Vec<FriPolynomialInfo { oracle_index, polynomial_index }> }"""
+
+    def __init__(self, point: Tuple[int, int], polynomials: Sequence[Tuple[int, int]]):
+        self.point = (int(point[0]), int(point[1]))
+        self.polynomials = [(int(o), int(i)) for (o, i) in polynomials]
+
+
+class FriProofHead:
+    """What prove_openings produces before the query rounds: FriProof { commit_phase_merkle_caps, final_poly, pow_witness };
+    `trees` are the commit-phase MerkleTrees the query rounds read with .get/.prove."""
+
+    def __init__(self, trees, final_poly, pow_witness, lde_final_len):
+        self.trees = trees
+        self.commit_phase_merkle_caps = [t.cap for t in trees]
+        self.final_poly = final_poly
+        self.pow_witness = pow_witness
+        self.lde_final_len = lde_final_len
+
+
+def prove_openings(instance: Sequence[FriBatchInfo], oracles: Sequence["PolynomialBatch"], challenger, fri_params: FriParams,
+                   proof_of_work_bits: Optional[int] = None, ctx: Optional[Context] = None, debug: Optional[dict] = None) -> FriProofHead:
+    """plonky2 fri/oracle.rs · PolynomialBatch::prove_openings up to (not including) the query rounds, on the device:
+    alpha <- challenger; per batch reduce_polys_base + divide_by_linear + shift_poly; final_poly.lde(rate_bits).coset_fft(7);
+    fri_committed_trees; fri_proof_of_work (if proof_of_work_bits is given).  The coefficient matrices of `oracles` never
+    leave HBM.  `debug` (a dict) receives final_poly / quotients / lde arrays for tests."""
+    ctx = ctx or default_context()
+    lib = ctx.lib
+    if not oracles:
+        raise ValueError("no oracles")
+    log_n = oracles[0].degree_log
+    alpha = challenger.get_extension_challenge()
+    al = np.array([int(alpha[0]), int(alpha[1])], dtype=np.uint64)
+    oh = c_uint64()
+    _check(ctx, lib.gl_openings_begin(ctx.handle, log_n, byref(oh)))
+    fh = c_uint64()
+    try:
+        for batch in instance:
+            hs = np.array([oracles[o].merkle_tree._h for (o, _) in batch.polynomials], dtype=np.uint64)
+            cs = np.array([i for (_, i) in batch.polynomials], dtype=np.uint32)
+            pt = np.array(batch.point, dtype=np.uint64)
+            q = np.zeros((1 << log_n, 2), dtype=np.uint64) if debug is not None else None
+            _check(ctx, lib.gl_openings_add_batch(ctx.handle, oh.value, _ptr(hs) if hs.size else None, _ptr(cs) if cs.size else None,
+                                                  hs.size, _ptr(al), _ptr(pt), _ptr(q)))
+            if debug is not None:
+                debug.setdefault("quotients", []).append(q)
+        if debug is not None:
+            fp = np.zeros((1 << log_n, 2), dtype=np.uint64)
+            _check(ctx, lib.gl_openings_final_poly(ctx.handle, oh.value, _ptr(fp)))
+            debug["final_poly"] = fp
+        _check(ctx, lib.gl_openings_lde(ctx.handle, oh.value, fri_params.rate_bits, fri_params.cap_height, byref(fh)))
+    finally:
+        lib.gl_openings_end(ctx.handle, oh.value)
+    try:
         n = c_uint64()
-        _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh.value, None, byref(n)))
-        final = np.zeros((n.value, 2), dtype=np.uint64)
-        _check(ctx, lib.gl_fri_final_poly(ctx.handle, fh.value, _ptr(final), byref(n)))
-        challenger.observe_extension_elements(final)
+        _check(ctx, lib.gl_fri_read(ctx.handle, fh.value, None, None, byref(n)))
+        if debug is not None:
+            co = np.zeros((n.value, 2), dtype=np.uint64)
+            va = np.zeros((n.value, 2), dtype=np.uint64)
+            _check(ctx, lib.gl_fri_read(ctx.handle, fh.value, _ptr(co), _ptr(va), byref(n)))
+            debug["lde_final_poly"], debug["lde_final_values_bitrev"] = co, va
+        trees, final = _fri_commit_phase(ctx, fh.value, challenger, fri_params)
     finally:
         lib.gl_fri_end(ctx.handle, fh.value)
-    return trees, final
+    w = fri_proof_of_work(challenger, proof_of_work_bits, ctx) if proof_of_work_bits is not None else None
+    return FriProofHead(trees, final, w, int(n.value))

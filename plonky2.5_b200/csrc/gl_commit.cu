@@ -20,6 +20,7 @@
 #include "merkle.cuh"
 #include "microbench.cuh"
 #include "ntt.cuh"
+#include "openings.cuh"
 
 namespace {
 
@@ -148,6 +149,11 @@ struct Fri {
     DevBuf coeffs, values, tmp;   // values are kept in bit-reversed order (what the next layer's leaves need)
 };
 
+struct Openings {
+    uint32_t log_n = 0;
+    DevBuf final_poly, comp, refs, pw;   // final_poly / composition: N extension elements each
+};
+
 }  // namespace
 
 struct gl_ctx {
@@ -160,6 +166,7 @@ struct gl_ctx {
     DevBuf in_stage, vals, scratch;
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
     std::map<gl_handle, std::unique_ptr<Fri>> fris;
+    std::map<gl_handle, std::unique_ptr<Openings>> openings;
     gl_handle next_handle = 1;
     cudaStream_t copy_stream = nullptr;   // host->device column copies of gl_commit, overlapped with the NTTs
     cudaEvent_t ev_sync = nullptr;
@@ -557,6 +564,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->trees.clear();
     c->fris.clear();
+    c->openings.clear();
     c->roots.clear();
     c->lde_tables.clear();
     c->in_stage.release(); c->vals.release(); c->scratch.release();
@@ -959,6 +967,147 @@ int gl_fri_end(gl_ctx* c, gl_handle fh) {
     find_fri(c, fh);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->fris.erase(fh);
+    return GL_OK;
+    GL_API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------------ prove_openings (front half)
+namespace {
+Openings* find_openings(gl_ctx* c, gl_handle h) {
+    auto it = c->openings.find(h);
+    if (it == c->openings.end()) GL_THROW(GL_ERR_HANDLE, "unknown openings handle %llu", (unsigned long long)h);
+    return it->second.get();
+}
+struct HExt { uint64_t a0, a1; };
+HExt h_ext_mul(HExt a, HExt b) {   // F_p[X]/(X^2 - 7)
+    uint64_t m11 = gl::h_mul(a.a1, b.a1);
+    HExt r;
+    r.a0 = (uint64_t)(((unsigned __int128)gl::h_mul(a.a0, b.a0) + gl::h_mul(m11, 7)) % gl::P);
+    r.a1 = (uint64_t)(((unsigned __int128)gl::h_mul(a.a0, b.a1) + gl::h_mul(a.a1, b.a0)) % gl::P);
+    return r;
+}
+}  // namespace
+
+int gl_openings_begin(gl_ctx* c, uint32_t log_n, gl_handle* out) {
+    GL_API_BEGIN(c)
+    if (!out) GL_THROW(GL_ERR_INVALID, "out_openings is NULL");
+    if (log_n > 30) GL_THROW(GL_ERR_UNSUPPORTED, "log_n = %u > 30", log_n);
+    auto o = std::make_unique<Openings>();
+    o->log_n = log_n;
+    const uint64_t n = 1ULL << log_n;
+    o->final_poly.ensure(2 * n);
+    o->comp.ensure(2 * n);
+    CUDA_CHECK(cudaMemsetAsync(o->final_poly.p, 0, 16 * n, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    gl_handle h = c->next_handle++;
+    c->openings[h] = std::move(o);
+    *out = h;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_openings_add_batch(gl_ctx* c, gl_handle oh, const gl_handle* batches, const uint32_t* columns, uint32_t n_polys,
+                          const uint64_t alpha[2], const uint64_t point[2], uint64_t* out_quotient) {
+    GL_API_BEGIN(c)
+    Openings* o = find_openings(c, oh);
+    if (!alpha || !point || (n_polys && (!batches || !columns))) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    const uint32_t n = 1u << o->log_n;
+    std::vector<openings::PolyRef> refs(n_polys);
+    std::vector<uint64_t> pw(2 * (size_t)n_polys);
+    const HExt al = {gl::canon(alpha[0]), gl::canon(alpha[1])};
+    HExt cur = {1, 0};
+    for (uint32_t j = 0; j < n_polys; j++) {
+        Tree* t = find_tree(c, batches[j]);
+        if (!t->has_coeffs) GL_THROW(GL_ERR_INVALID, "polynomial %u: the tree has no coefficients", j);
+        if (t->degree_log != o->log_n) GL_THROW(GL_ERR_INVALID, "Polynomial degrees inconsistent (polynomial %u has degree_log %u, expected %u)",
+                                                j, t->degree_log, o->log_n);
+        if (columns[j] >= t->leaf_len) GL_THROW(GL_ERR_INVALID, "polynomial %u: column %u out of range", j, columns[j]);
+        refs[j] = {t->coeffs.p, t->pitch, columns[j]};
+        pw[2 * j] = cur.a0; pw[2 * j + 1] = cur.a1;
+        cur = h_ext_mul(cur, al);
+    }
+    // cur = alpha^n_polys: what shift_poly multiplies the running final_poly by
+    if (n_polys) {
+        static_assert(sizeof(openings::PolyRef) == 16, "PolyRef is two words");
+        o->refs.ensure(2 * (size_t)n_polys);
+        o->pw.ensure(2 * (size_t)n_polys);
+        CUDA_CHECK(cudaMemcpyAsync(o->refs.p, refs.data(), 16 * (size_t)n_polys, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(o->pw.p, pw.data(), 16 * (size_t)n_polys, cudaMemcpyHostToDevice, c->stream));
+        openings::reduce_polys_base_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(
+            reinterpret_cast<const openings::PolyRef*>(o->refs.p), reinterpret_cast<const ulonglong2*>(o->pw.p), n_polys, n,
+            reinterpret_cast<ulonglong2*>(o->comp.p));
+        CUDA_CHECK(cudaGetLastError());
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(o->comp.p, 0, 16 * (size_t)n, c->stream));
+    }
+    const uint32_t threads = n < 1024 ? n : 1024;
+    openings::divide_by_linear_kernel<<<1, threads, 0, c->stream>>>(reinterpret_cast<ulonglong2*>(o->comp.p), n, gl::canon(point[0]),
+                                                                    gl::canon(point[1]));
+    CUDA_CHECK(cudaGetLastError());
+    openings::shift_add_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<ulonglong2*>(o->final_poly.p),
+                                                                      reinterpret_cast<const ulonglong2*>(o->comp.p), n, cur.a0, cur.a1);
+    CUDA_CHECK(cudaGetLastError());
+    if (out_quotient) CUDA_CHECK(cudaMemcpyAsync(out_quotient, o->comp.p, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // refs / pw are host vectors of this call
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_openings_final_poly(gl_ctx* c, gl_handle oh, uint64_t* out) {
+    GL_API_BEGIN(c)
+    Openings* o = find_openings(c, oh);
+    if (!out) GL_THROW(GL_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaMemcpyAsync(out, o->final_poly.p, 16ULL << o->log_n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_openings_lde(gl_ctx* c, gl_handle oh, uint32_t rate_bits, uint32_t cap_height, gl_handle* out_fri) {
+    GL_API_BEGIN(c)
+    Openings* o = find_openings(c, oh);
+    if (!out_fri) GL_THROW(GL_ERR_INVALID, "out_fri is NULL");
+    if (o->log_n + rate_bits > 31) GL_THROW(GL_ERR_UNSUPPORTED, "log_n + rate_bits = %u > 31", o->log_n + rate_bits);
+    const uint64_t n = 1ULL << o->log_n, len = n << rate_bits;
+    auto f = std::make_unique<Fri>();
+    f->len = len; f->rate_bits = rate_bits; f->cap_height = cap_height;
+    f->coeffs.ensure(2 * len); f->values.ensure(2 * len); f->tmp.ensure(2 * len);
+    // final_poly.lde(rate_bits): zero-padded coefficients; values = coset_fft(shift 7), kept bit-reversed (in-place DIF order)
+    CUDA_CHECK(cudaMemsetAsync(f->coeffs.p, 0, 16 * len, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(f->coeffs.p, o->final_poly.p, 16 * n, cudaMemcpyDeviceToDevice, c->stream));
+    const uint32_t log_len = o->log_n + rate_bits;
+    if (log_len == 0) {
+        CUDA_CHECK(cudaMemcpyAsync(f->values.p, f->coeffs.p, 16, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        CosetTable tab;
+        fill_coset_table(c, tab, gl::COSET_SHIFT, log_len);
+        run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, &tab, 2, nullptr);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // tab is released at scope exit
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    gl_handle h = c->next_handle++;
+    c->fris[h] = std::move(f);
+    *out_fri = h;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_openings_end(gl_ctx* c, gl_handle oh) {
+    GL_API_BEGIN(c)
+    find_openings(c, oh);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->openings.erase(oh);
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_fri_read(gl_ctx* c, gl_handle fh, uint64_t* out_coeffs, uint64_t* out_values, uint64_t* out_len) {
+    GL_API_BEGIN(c)
+    Fri* f = find_fri(c, fh);
+    if (out_len) *out_len = f->len;
+    if (out_coeffs) CUDA_CHECK(cudaMemcpyAsync(out_coeffs, f->coeffs.p, 16 * f->len, cudaMemcpyDeviceToHost, c->stream));
+    if (out_values) CUDA_CHECK(cudaMemcpyAsync(out_values, f->values.p, 16 * f->len, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return GL_OK;
     GL_API_END(c)
 }

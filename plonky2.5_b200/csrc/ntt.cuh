@@ -191,7 +191,7 @@ ntt_pass_kernel(const PassParams p) {   // >= 48 resident warps per SM where the
             v = gl::mul(v, w);
         }
         if (p.scale != 1) v = gl::mul(v, p.scale);
-        v = gl::canon(v);
+        if (!b_lo) v = gl::canon(v);   // only what leaves the NTT is canonical; between passes any 64-bit representative will do
         uint32_t prow = row_base | (l << b_lo);
         if (p.store_mode == 2) {
             if (col >= p.scatter_ncols) continue;

@@ -66,6 +66,8 @@ class OracleC:
         L.glo_root_of_unity.argtypes = [ctypes.c_uint]
         L.glo_mul.restype = u64
         L.glo_mul.argtypes = [u64, u64]
+        L.glo_openings_add_batch.restype = ctypes.c_int
+        L.glo_openings_add_batch.argtypes = [ctypes.POINTER(vp), ctypes.c_uint32, u64, vp, vp, vp, vp]
 
     def set_threads(self, n):
         self.lib.glo_set_num_threads(int(n))
@@ -144,6 +146,23 @@ class OracleC:
 
     def new_challenger(self):
         return ChallengerC(self)
+
+    def openings_final_poly(self, batches, oracles, alpha):
+        """batches: [(point (a0, a1), [(oracle_index, polynomial_index), ...])]; oracles: [n_cols][N] uint64 arrays.
+        Returns (final_poly [N][2], [quotient [N][2] per batch]) — prove_openings front half."""
+        n = np.asarray(oracles[0]).shape[1]
+        final = np.zeros((n, 2), dtype=np.uint64)
+        quotients = []
+        al = np.array(alpha, dtype=np.uint64)
+        for point, polys in batches:
+            cols = [np.ascontiguousarray(oracles[o][i], dtype=np.uint64) for (o, i) in polys]
+            ptrs = (vp * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+            q = np.zeros((n, 2), dtype=np.uint64)
+            pt = np.array(point, dtype=np.uint64)
+            rc = self.lib.glo_openings_add_batch(ptrs, len(cols), n, al.ctypes.data, pt.ctypes.data, final.ctypes.data, q.ctypes.data)
+            assert rc == 0
+            quotients.append(q)
+        return final, quotients
 
     def fri_committed_trees(self, coeffs, values, arity_bits, rate_bits, cap_height, challenger):
         co = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 2)

@@ -272,3 +272,60 @@ def test_fri_proof_of_work_matches_oracle(ctx, oc, bits):
     wb = b.fri_proof_of_work(bits)
     assert wa == wb
     assert a.get_challenge() == b.get_challenge()
+
+
+# ---- prove_openings, front half ---------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(3, [3, 2], 1, 1, []), (6, [9, 5, 2, 2], 3, 2, [2]), (10, [135, 20], 3, 4, [4]), (12, [86, 135, 20, 16], 3, 4, [4, 4]),
+                                 (0, [2], 2, 0, [])])
+def test_prove_openings_front_half_matches_oracle(ctx, oc, cfg):
+    """commits -> prove_openings(instance) on the device: per-batch quotients, final_poly, its LDE, the FRI commit phase and the
+    proof-of-work witness equal the oracle's (same transcript), for plonky2-shaped instances (all polynomials at zeta, a few at g*zeta)."""
+    g = _g()
+    log_n, widths, r, cap_h, arities = cfg
+    n = 1 << log_n
+    rng = random.Random(log_n * 31 + len(widths))
+    cols = [splitmix_columns(900 + 17 * k + log_n, w, n) for k, w in enumerate(widths)]
+    batches = [g.PolynomialBatch.from_values(list(c), r, False, min(cap_h, log_n + r), ctx=ctx) for c in cols]
+    coeffs = [b.polynomials for b in batches]
+    zeta = (rng.randrange(P), rng.randrange(P))
+    gz = (rng.randrange(P), rng.randrange(P))
+    all_polys = [(k, i) for k, w in enumerate(widths) for i in range(w)]
+    instance = [g.FriBatchInfo(zeta, all_polys), g.FriBatchInfo(gz, [(len(widths) - 1, i) for i in range(min(2, widths[-1]))])]
+    ch_ref, ch_gpu = oc.new_challenger(), g.Challenger(ctx)     # the product's own challenger mirror (needed by the PoW grind)
+    for ch in (ch_ref, ch_gpu):
+        ch.observe_elements([5, 6, 7, 8, 9])
+    # reference transcript
+    alpha = ch_ref.get_extension_challenge()
+    final_ref, quot_ref = oc.openings_final_poly([(b.point, b.polynomials) for b in instance], coeffs, alpha)
+    lde = np.zeros((n << r, 2), dtype=np.uint64)
+    lde[:n] = final_ref
+    vals = np.stack([oc.coset_fft(lde[:, 0], 7), oc.coset_fft(lde[:, 1], 7)], axis=1)
+    ref = oc.fri_committed_trees(lde, vals, arities, r, min(cap_h, log_n + r), ch_ref)
+    w_ref = ch_ref.fri_proof_of_work(8)
+    # product
+    dbg = {}
+    head = g.prove_openings(instance, batches, ch_gpu, g.FriParams(r, min(cap_h, log_n + r), arities), proof_of_work_bits=8, ctx=ctx, debug=dbg)
+    for q, qr in zip(dbg["quotients"], quot_ref):
+        assert np.array_equal(q, qr)
+    assert np.array_equal(dbg["final_poly"], final_ref)
+    assert np.array_equal(dbg["lde_final_poly"], lde)
+    bits = log_n + r
+    rev = np.array([int(format(i, "0%db" % bits)[::-1], 2) if bits else 0 for i in range(n << r)])
+    assert np.array_equal(dbg["lde_final_values_bitrev"], vals[rev])
+    assert len(head.trees) == len(arities)
+    for t, cap in zip(head.trees, ref["caps"]):
+        assert np.array_equal(t.cap.hashes, cap)
+    assert np.array_equal(head.final_poly, ref["final_poly"])
+    assert head.pow_witness == w_ref
+    assert ch_ref.get_challenge() == ch_gpu.get_challenge()
+
+
+def test_prove_openings_errors(ctx):
+    g = _g()
+    a = g.PolynomialBatch.from_values(list(splitmix_columns(1, 3, 8)), 1, False, 1, ctx=ctx)
+    b = g.PolynomialBatch.from_values(list(splitmix_columns(2, 3, 16)), 1, False, 1, ctx=ctx)
+    ch = g.Challenger(ctx)
+    with pytest.raises(ValueError, match="Polynomial degrees inconsistent"):
+        g.prove_openings([g.FriBatchInfo((1, 2), [(0, 0), (1, 0)])], [a, b], ch, g.FriParams(1, 1, []), ctx=ctx)
+    with pytest.raises(ValueError, match="out of range"):
+        g.prove_openings([g.FriBatchInfo((1, 2), [(0, 3)])], [a], ch, g.FriParams(1, 1, []), ctx=ctx)

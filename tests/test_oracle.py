@@ -245,3 +245,65 @@ def test_pow_c_matches_python_and_is_smallest(oc):
             st = list(base); st[pos] = w
             assert 64 - o.poseidon(st)[7].bit_length() < bits
         assert a.get_challenge() == b.get_challenge()
+
+
+# ---- prove_openings, front half: the two restatements agree and satisfy the defining identities ------------------------
+def _openings_case(seed, log_n, widths, batches_spec):
+    rng = random.Random(seed)
+    n = 1 << log_n
+    oracles = [splitmix_columns(seed * 7 + k, w, n) for k, w in enumerate(widths)]
+    batches = []
+    for polys in batches_spec:
+        point = (rng.randrange(o.P), rng.randrange(o.P))
+        batches.append((point, polys))
+    alpha = (rng.randrange(o.P), rng.randrange(o.P))
+    return oracles, batches, alpha
+
+
+OPENINGS_CASES = [
+    (1, 3, [3, 2], [[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1)], [(1, 1)]]),
+    (2, 5, [4], [[(0, 3), (0, 1)], [(0, 0)], [(0, 2), (0, 2), (0, 0)]]),
+    (3, 0, [2], [[(0, 0), (0, 1)]]),
+    (4, 6, [9, 5, 2, 2], [[(0, i) for i in range(9)] + [(1, i) for i in range(5)] + [(2, 0), (2, 1), (3, 0), (3, 1)], [(2, 0), (2, 1)]]),
+]
+
+
+@pytest.mark.parametrize("case", OPENINGS_CASES)
+def test_openings_front_half_restatements_agree(oc, case):
+    oracles, batches, alpha = _openings_case(*case)
+    final_py, quot_py = o.prove_openings_final_poly(batches, [[list(map(int, c)) for c in orc] for orc in oracles], alpha)
+    final_c, quot_c = oc.openings_final_poly(batches, oracles, alpha)
+    assert [list(map(int, r)) for r in final_c] == [list(e) for e in final_py]
+    for qc, qp in zip(quot_c, quot_py):
+        assert [list(map(int, r)) for r in qc] == [list(e) for e in qp]
+
+
+@pytest.mark.parametrize("case", OPENINGS_CASES)
+def test_openings_front_half_identities(case):
+    """(X - z) * quotient + F(z) == F with F = sum_j alpha^j f_j, and final = sum_i alpha^(polys after batch i) * quotient_i."""
+    oracles, batches, alpha = _openings_case(*case)
+    orc = [[list(map(int, c)) for c in x] for x in oracles]
+    final, quots = o.prove_openings_final_poly(batches, orc, alpha)
+    n = len(orc[0][0])
+    later = 0
+    expect = [(0, 0)] * n
+    for (point, polys), q in reversed(list(zip(batches, quots))):
+        F = [(0, 0)] * n
+        for j, (oi, pi) in enumerate(polys):
+            F = [o.ext_add(a, o.ext_scale(o.ext_pow(alpha, j), c)) for a, c in zip(F, orc[oi][pi])]
+        Fz = o.ext_eval_poly_ext(F, point)
+        assert q[-1] == (0, 0)
+        back = [(0, 0)] * n                      # (X - z) * q
+        for k in range(n - 1):
+            back[k + 1] = o.ext_add(back[k + 1], q[k])
+            back[k] = o.ext_sub(back[k], o.ext_mul(point, q[k]))
+        back[0] = o.ext_add(back[0], Fz)
+        assert back == F
+        s = o.ext_pow(alpha, later)
+        expect = [o.ext_add(e, o.ext_mul(s, c)) for e, c in zip(expect, q)]
+        later += len(polys)
+    assert expect == final
+    lde, vals = o.prove_openings_lde(final, 2)
+    x = o.MULTIPLICATIVE_GROUP_GENERATOR * pow(o.primitive_root_of_unity(o.log2_strict(len(lde))), 3, o.P) % o.P if len(lde) > 4 else None
+    if x is not None:
+        assert vals[3] == o.ext_eval_poly(final, x)
