@@ -282,9 +282,7 @@ def main():
             harr.copy_(d_cols)
 
             def e2e_step():
-                d = harr.to(dev, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                cap[:] = state.commit(d)
+                cap[:] = state.commit_host(harr)     # fused mode: chunked H2D behind the NTTs (gl_lde_scatter)
             h2d = (c1 - c0) * n * 8
         for _ in range(2):
             e2e_step()
@@ -305,7 +303,7 @@ def main():
         e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
-                      if world == 1 else "pinned host shard -> device, sharded commit, cap to host"}
+                      if world == 1 else "ShardedCommit.commit_host: pinned host shard -> gl_lde_scatter (chunked H2D overlapped with the NTTs) -> hash -> cap to host"}
 
     if world > 1:
         if os.environ.get("GL_BENCH_PHASES"):

@@ -161,6 +161,11 @@ int gl_dev_lde_scatter(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride,
                        uint32_t rate_bits, int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers,
                        uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch,
                        uint32_t first_coset);
+/* the same with HOST columns (cols[j] = N words, as gl_commit): the shard is copied in growing chunks on a copy stream while
+ * the NTTs of the previous chunk run, so only the first 8-column copy is exposed                                        */
+int gl_lde_scatter(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                   int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
+                   uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset);
 /* CUDA IPC plumbing for the above: export a device buffer (64-byte handle) / map a peer's / unmap / free */
 int gl_dev_ipc_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]);
 int gl_dev_ipc_open(gl_ctx* ctx, const uint8_t handle[64], uint64_t** out_ptr);

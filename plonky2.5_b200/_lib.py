@@ -58,6 +58,8 @@ SIGNATURES = {
     "gl_dev_lde": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_int, c_void_p, c_uint32, c_void_p]),
     "gl_dev_lde_scatter": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_int, POINTER(c_void_p), c_uint32,
                                    c_uint32, c_uint32, c_void_p, c_uint32, c_uint32]),
+    "gl_lde_scatter": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_int, POINTER(c_void_p), c_uint32,
+                               c_uint32, c_uint32, c_void_p, c_uint32, c_uint32]),
     "gl_dev_ipc_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), c_void_p]),
     "gl_dev_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "gl_dev_ipc_close": (c_int, [c_void_p, c_void_p]),

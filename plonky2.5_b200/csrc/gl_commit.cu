@@ -395,6 +395,8 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
         if (scatter) {   // d_rows is an [N][row_pitch] scratch reused by every coset (stream order)
             ntt::Scatter sc = *scatter;
             sc.row0 = (uint64_t)h_bitrev(s, rate_bits) * N;
+            sc.col0 = scatter->col0 + col0;   // this chunk's columns inside the leaf row
+            sc.ncols = n_cols;
             run_ntt(c, coeffs, coeff_pitch, d_rows + col0, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld, &sc);
         } else {
             uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch + col0;
@@ -411,6 +413,35 @@ void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
     if (!is_coeffs) c->vals.ensure(((uint64_t)1 << log_n) * coeff_pitch);
     lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, is_coeffs, c->vals.p, d_coeffs, coeff_pitch, d_rows,
                 row_pitch, G, timed, timed);
+}
+
+// Host columns -> c->in_stage in chunks on the copy stream; fn(c0, nc, first) runs on the compute stream once chunk
+// [c0, c0 + nc) has landed, i.e. transpose + iNTT + LDE of chunk k overlap the PCIe copy of chunk k+1 (column groups are
+// independent polynomials).  Chunks grow 8, 16, 24, 24, ... columns: only the small first copy is exposed.  Chunk offsets
+// are multiples of 8.  With pinned host memory the copies overlap completely.
+template <class F>
+void for_each_host_chunk(gl_ctx* c, const uint64_t* const* host_cols, uint32_t n_cols, uint64_t N, F&& fn) {
+    for (uint32_t j = 0; j < n_cols; j++)
+        if (!host_cols[j]) GL_THROW(GL_ERR_INVALID, "cols[%u] is NULL", j);
+    c->in_stage.ensure(N * n_cols);
+    std::vector<std::pair<uint32_t, uint32_t>> chunks;
+    for (uint32_t c0 = 0, sz = 8; c0 < n_cols; c0 += sz, sz = std::min(sz + 8, 24u)) chunks.push_back({c0, std::min(sz, n_cols - c0)});
+    if (c->chunk_ev.size() < chunks.size()) {
+        size_t old = c->chunk_ev.size();
+        c->chunk_ev.resize(chunks.size(), nullptr);
+        for (size_t i = old; i < chunks.size(); i++) CUDA_CHECK(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));              // in_stage may still be read by an earlier call
+    CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
+    for (size_t k = 0; k < chunks.size(); k++) {
+        for (uint32_t j = chunks[k].first; j < chunks[k].first + chunks[k].second; j++)
+            CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, host_cols[j], N * 8, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_CHECK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
+    }
+    for (size_t k = 0; k < chunks.size(); k++) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[k], 0));
+        fn(chunks[k].first, chunks[k].second, k == 0);
+    }
 }
 
 int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_cols_in, uint64_t col_stride, uint32_t n_cols,
@@ -436,36 +467,13 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
 
     record(c, GL_STAGE_H2D);
     if (host_cols) {
-        // Host columns: copy in chunks of CHUNK columns on the copy stream and run transpose + iNTT + LDE of chunk k on the
-        // compute stream while chunk k+1 is still crossing PCIe (column groups are independent polynomials).  With pinned
-        // host memory the copies overlap completely; the stage split then reads h2d = first chunk, lde = everything else.
-        constexpr uint32_t CHUNK = 24;
-        for (uint32_t j = 0; j < n_cols; j++)
-            if (!host_cols[j]) GL_THROW(GL_ERR_INVALID, "cols[%u] is NULL", j);
-        c->in_stage.ensure(N * n_cols);
         if (!is_coeffs) c->vals.ensure(N * pitch);
-        const uint32_t n_chunks = (n_cols + CHUNK - 1) / CHUNK;
-        if (c->chunk_ev.size() < n_chunks) {
-            size_t old = c->chunk_ev.size();
-            c->chunk_ev.resize(n_chunks, nullptr);
-            for (size_t i = old; i < n_chunks; i++) CUDA_CHECK(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
-        }
-        CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));              // in_stage may still be read by an earlier call
-        CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
-        for (uint32_t k = 0; k < n_chunks; k++) {
-            const uint32_t c0 = k * CHUNK, nc = std::min(CHUNK, n_cols - c0);
-            for (uint32_t j = c0; j < c0 + nc; j++)
-                CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, host_cols[j], N * 8, cudaMemcpyHostToDevice, c->copy_stream));
-            CUDA_CHECK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
-        }
-        for (uint32_t k = 0; k < n_chunks; k++) {
-            const uint32_t c0 = k * CHUNK, nc = std::min(CHUNK, n_cols - c0);
+        for_each_host_chunk(c, host_cols, n_cols, N, [&](uint32_t c0, uint32_t nc, bool first) {
             const uint32_t width = std::min(round_up(nc, 8), pitch - c0);
-            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[k], 0));
-            if (k == 0) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); }
+            if (first) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); }   // h2d = first chunk
             lde_columns(c, c->in_stage.p + (uint64_t)c0 * N, N, c0, nc, width, log_n, rate_bits, is_coeffs, c->vals.p, t->coeffs.p, pitch,
                         t->leaves.p, pitch, 8, true, false);
-        }
+        });
     } else {
         record(c, GL_STAGE_TRANSPOSE);
         lde_stage(c, d_cols_in, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
@@ -620,12 +628,11 @@ int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
     GL_API_END(c)
 }
 
-int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
-                       int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
-                       uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset) {
-    GL_API_BEGIN(c)
+static int lde_scatter_impl(gl_ctx* c, const uint64_t* d_cols, const uint64_t* const* host_cols, uint64_t col_stride, uint32_t n_cols,
+                            uint32_t log_n, uint32_t rate_bits, int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers,
+                            uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset) {
     check_shape(n_cols, log_n, rate_bits, 0);
-    if (!d_cols || !peer_leaves || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if ((!d_cols && !host_cols) || !peer_leaves || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
     if (n_peers == 0 || (n_peers & (n_peers - 1)) || n_peers > ntt::MAX_PEERS) GL_THROW(GL_ERR_INVALID, "n_peers must be a power of two <= %d", ntt::MAX_PEERS);
     const uint64_t N = 1ULL << log_n, R = N << rate_bits;
     if (R < n_peers) GL_THROW(GL_ERR_INVALID, "fewer leaf rows than peers");
@@ -647,14 +654,43 @@ int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, u
     c->scratch.ensure(N * coeff_pitch);      // pass scratch of one coset
     if (!input_is_coeffs) c->vals.ensure(N * coeff_pitch);
     for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
-    record(c, GL_STAGE_TRANSPOSE);
-    lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch,
-                c->scratch.p, coeff_pitch, G, true, true, &sc, first_coset);
+    if (host_cols) {
+        record(c, GL_STAGE_H2D);
+        for_each_host_chunk(c, host_cols, n_cols, N, [&](uint32_t c0, uint32_t nc, bool first) {
+            const uint32_t width = std::min(round_up(nc, (uint32_t)G), coeff_pitch - c0);
+            if (first) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); }
+            lde_columns(c, c->in_stage.p + (uint64_t)c0 * N, N, c0, nc, width, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs,
+                        coeff_pitch, c->scratch.p, coeff_pitch, G, true, false, &sc, first_coset);
+        });
+    } else {
+        record(c, GL_STAGE_TRANSPOSE);
+        lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch,
+                    c->scratch.p, coeff_pitch, G, true, true, &sc, first_coset);
+    }
     record(c, GL_STAGE_LEAF_HASH);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
-        CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
+        if (host_cols || i != GL_STAGE_H2D) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     return GL_OK;
+}
+
+int gl_dev_lde_scatter(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                       int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
+                       uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset) {
+    GL_API_BEGIN(c)
+    if (!d_cols) GL_THROW(GL_ERR_INVALID, "d_cols is NULL");
+    return lde_scatter_impl(c, d_cols, nullptr, col_stride, n_cols, log_n, rate_bits, input_is_coeffs, peer_leaves, n_peers, leaf_pitch,
+                            col_off, d_out_coeffs, coeff_pitch, first_coset);
+    GL_API_END(c)
+}
+
+int gl_lde_scatter(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, int input_is_coeffs,
+                   uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs,
+                   uint32_t coeff_pitch, uint32_t first_coset) {
+    GL_API_BEGIN(c)
+    if (!cols) GL_THROW(GL_ERR_INVALID, "cols is NULL");
+    return lde_scatter_impl(c, nullptr, cols, 0, n_cols, log_n, rate_bits, input_is_coeffs, peer_leaves, n_peers, leaf_pitch, col_off,
+                            d_out_coeffs, coeff_pitch, first_coset);
     GL_API_END(c)
 }
 

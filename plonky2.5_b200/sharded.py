@@ -221,6 +221,25 @@ class ShardedCommit:
             off += p.rows_per_rank * p.pitches[q]
         return self._hash()
 
+    def commit_host(self, h_cols) -> np.ndarray:
+        """The same commit from HOST columns: h_cols = this rank's [n_cols_g][N] tensor in (ideally pinned) host memory.  In the
+        fused mode the shard crosses PCIe in chunks behind the NTTs of the previous chunk (gl_lde_scatter)."""
+        p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
+        n = 1 << p.log_n
+        ncg = p.col_counts[self.rank]
+        assert tuple(h_cols.shape) == (ncg, n) and h_cols.is_contiguous() and not h_cols.is_cuda
+        if self.exchange != "p2p":
+            d = h_cols.to(torch.device("cuda", self.ctx.device), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self.commit(d)
+        base = h_cols.data_ptr()
+        ptrs = (ctypes.c_void_p * ncg)(*[base + 8 * n * j for j in range(ncg)])
+        self._check(lib.gl_lde_scatter(h, ptrs, ncg, p.log_n, p.rate_bits, 0, self._peer_ptrs, p.world, p.leaf_pitch,
+                                       p.col_offsets[self.rank], self.coeffs.data_ptr(), p.pitches[self.rank], self._first_coset))
+        with torch.cuda.stream(self._stream):
+            self.dist.all_reduce(self._flag)
+        return self._hash()
+
     def _hash(self) -> np.ndarray:
         p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
         import time

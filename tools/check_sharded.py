@@ -37,7 +37,7 @@ def main():
         for mode in ("p2p", "nccl"):
             sc = ShardedCommit(ctx, plan, rank, dist, torch, exchange=mode)
             cap = sc.commit(d).reshape(-1, 4)
-            cap2 = sc.commit(d).reshape(-1, 4)          # buffers are reused: a second commit must give the same cap
+            cap2 = sc.commit_host(torch.from_numpy(x[c0:c1].view(np.int64).copy()).pin_memory()).reshape(-1, 4)   # host-column path; buffers reused
             dig = sc.digests.cpu().numpy().view(np.uint64)[:plan.digests_per_rank() * 4].reshape(-1, 4)
             want_dig = ref["digests"][rank * plan.digests_per_rank():(rank + 1) * plan.digests_per_rank()]
             good = np.array_equal(cap, ref["cap"]) and np.array_equal(cap2, ref["cap"]) and np.array_equal(dig, want_dig)
