@@ -8,10 +8,12 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <utility>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -169,6 +171,21 @@ struct gl_ctx {
     std::map<gl_handle, std::unique_ptr<Openings>> openings;
     gl_handle next_handle = 1;
     cudaStream_t copy_stream = nullptr;   // host->device column copies of gl_commit, overlapped with the NTTs
+    // multi-GPU exchange mode of gl_*_lde_scatter (GL_SCATTER_MODE overrides; DESIGN.md §6 has the measurements):
+    //   0 = the last NTT pass stores every leaf-row segment into its owner's buffer itself (one kernel; 32/64-byte remote stores)
+    //   1 = the coset result stays local and a copy kernel on the high-priority send_stream ships it behind the next coset's NTT
+    //   2 = as 1 without overlap (measurement aid)
+    //   3 = default: cosets owned by this rank are stored by the NTT itself (no copy); the others stay local and the COPY ENGINES
+    //       ship them (one strided 2-D peer copy per owner segment) while the next coset's NTT runs — no SM time, no NVLink
+    //       stalls inside the NTT
+    int scatter_mode = 3;
+    cudaStream_t send_stream = nullptr;
+    cudaEvent_t ev_ntt[2] = {}, ev_sent[2] = {};
+    bool sent_pending[2] = {false, false};
+    DevBuf send_buf[2];
+    std::set<const uint64_t*> own_ipc;    // buffers exported by gl_dev_ipc_alloc (to tell the local leaf buffer from mapped peers)
+    bool trace = false;                    // GL_TRACE=1: per-coset timeline of the overlapped exchange on stderr (development aid)
+    std::vector<cudaEvent_t> trace_ev;     // base, then per coset: ntt start, ntt end, send start, send end
     cudaEvent_t ev_sync = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t ev[GL_N_STAGES + 1] = {};
@@ -397,7 +414,55 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
             sc.row0 = (uint64_t)h_bitrev(s, rate_bits) * N;
             sc.col0 = scatter->col0 + col0;   // this chunk's columns inside the leaf row
             sc.ncols = n_cols;
-            run_ntt(c, coeffs, coeff_pitch, d_rows + col0, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld, &sc);
+            // rows of this coset that live in this rank's own leaf buffer need no shipment: the NTT stores them itself
+            const bool all_local = scatter->self < ntt::MAX_PEERS && (sc.row0 >> sc.log_rows_per_peer) == scatter->self &&
+                                   ((sc.row0 + N - 1) >> sc.log_rows_per_peer) == scatter->self;
+            if (c->scatter_mode == 0 || (c->scatter_mode == 3 && all_local)) {
+                run_ntt(c, coeffs, coeff_pitch, d_rows + col0, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld, &sc);
+            } else {
+                // coset result into one of two local buffers; the copy kernel ships it on send_stream while the next coset's
+                // NTT runs on the compute stream (the buffer is reused only after its previous shipment has finished)
+                const int b = (int)(k & 1);
+                uint64_t* buf = c->send_buf[b].p + col0;
+                if (c->sent_pending[b]) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_sent[b], 0));
+                auto mark = [&](cudaStream_t st) {
+                    if (!c->trace) return;
+                    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); c->trace_ev.push_back(e);
+                };
+                if (c->trace && c->trace_ev.empty()) mark(c->stream);
+                mark(c->stream);
+                run_ntt(c, coeffs, coeff_pitch, buf, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
+                mark(c->stream);
+                CUDA_CHECK(cudaEventRecord(c->ev_ntt[b], c->stream));
+                if (c->scatter_mode != 2) CUDA_CHECK(cudaStreamWaitEvent(c->send_stream, c->ev_ntt[b], 0));
+                cudaStream_t ss = c->scatter_mode == 2 ? c->stream : c->send_stream;   // 2: no overlap (measurement aid)
+                mark(ss);
+                const uint32_t words = round_up(n_cols, 2);                            // a padding column may ride along
+                if (c->scatter_mode == 3) {
+                    // copy engines: one strided 2-D peer copy per owner segment of this coset (no SM time at all)
+                    const uint64_t rpp = 1ULL << sc.log_rows_per_peer;
+                    for (uint64_t r = 0; r < N;) {
+                        const uint64_t grow = sc.row0 + r, owner = grow >> sc.log_rows_per_peer, lrow = grow & (rpp - 1);
+                        const uint64_t cnt = std::min<uint64_t>(N - r, rpp - lrow);
+                        CUDA_CHECK(cudaMemcpy2DAsync(sc.peer[owner] + lrow * sc.pitch + sc.col0, (size_t)sc.pitch * 8, buf + r * row_pitch,
+                                                     (size_t)row_pitch * 8, (size_t)n_cols * 8, cnt, cudaMemcpyDefault, ss));
+                        r += cnt;
+                    }
+                } else if (row_pitch % 2 == 0 && sc.pitch % 2 == 0 && sc.col0 % 2 == 0 && sc.col0 + words <= sc.pitch && words / 2 <= 256 && N < (1ULL << 32)) {
+                    const uint32_t n_vec = words / 2, lane_rows = 256 / n_vec;
+                    const uint32_t blocks = (uint32_t)std::min<uint64_t>((N + lane_rows - 1) / lane_rows, (uint64_t)c->sm_count * 2);
+                    ntt::scatter_copy16_kernel<<<blocks, 256, 0, ss>>>(reinterpret_cast<const ulonglong2*>(buf), row_pitch / 2, n_vec, (uint32_t)N, sc);
+                } else {
+                    const uint64_t total = N * n_cols;
+                    const uint32_t blocks = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 4);
+                    ntt::scatter_copy_kernel<<<blocks, 256, 0, ss>>>(buf, row_pitch, n_cols, N, sc);
+                }
+                CUDA_CHECK(cudaGetLastError());
+                mark(ss);
+                if (l_ld) (*l_ld)++;
+                CUDA_CHECK(cudaEventRecord(c->ev_sent[b], ss));
+                c->sent_pending[b] = true;
+            }
         } else {
             uint64_t* dst = d_rows + (uint64_t)h_bitrev(s, rate_bits) * N * row_pitch + col0;
             run_ntt(c, coeffs, coeff_pitch, dst, row_pitch, cols_padded, log_n, false, &tabs[s], G, l_ld);
@@ -519,6 +584,7 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
         (ctx)->err = e.msg;                      \
         cudaGetLastError();                      \
         if ((ctx)->copy_stream) cudaStreamSynchronize((ctx)->copy_stream); /* host buffers are only borrowed */ \
+        if ((ctx)->send_stream) cudaStreamSynchronize((ctx)->send_stream);                                      \
         return e.code;                           \
     }                                            \
     catch (const std::bad_alloc&) {              \
@@ -558,6 +624,16 @@ int gl_ctx_create(gl_ctx** out, int device) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    {
+        int lo = 0, hi = 0;   // the shipment's few CTAs must get SM slots as NTT CTAs retire, not queue behind the whole NTT grid
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->send_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    }
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&c->ev_ntt[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_sent[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    if (const char* m = getenv("GL_SCATTER_MODE")) c->scatter_mode = atoi(m);
+    if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
     if (cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
@@ -581,6 +657,9 @@ void gl_ctx_destroy(gl_ctx* c) {
     for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->send_stream) { cudaStreamSynchronize(c->send_stream); cudaStreamDestroy(c->send_stream); }
+    for (int i = 0; i < 2; i++) { if (c->ev_ntt[i]) cudaEventDestroy(c->ev_ntt[i]); if (c->ev_sent[i]) cudaEventDestroy(c->ev_sent[i]); }
+    c->send_buf[0].release(); c->send_buf[1].release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -649,10 +728,14 @@ static int lde_scatter_impl(gl_ctx* c, const uint64_t* d_cols, const uint64_t* c
     sc.col0 = col_off;
     sc.pitch = leaf_pitch;
     sc.ncols = n_cols;
+    sc.self = ntt::MAX_PEERS;                 // which peer buffer is this rank's own (allocated by gl_dev_ipc_alloc on this context)?
+    for (uint32_t q = 0; q < n_peers; q++)
+        if (c->own_ipc.count(peer_leaves[q])) { sc.self = q; break; }
     get_roots(c, log_n);
     get_lde_tables(c, log_n, rate_bits);
     c->scratch.ensure(N * coeff_pitch);      // pass scratch of one coset
     if (!input_is_coeffs) c->vals.ensure(N * coeff_pitch);
+    if (c->scatter_mode) { c->send_buf[0].ensure(N * coeff_pitch); c->send_buf[1].ensure(N * coeff_pitch); }
     for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
     if (host_cols) {
         record(c, GL_STAGE_H2D);
@@ -667,8 +750,21 @@ static int lde_scatter_impl(gl_ctx* c, const uint64_t* d_cols, const uint64_t* c
         lde_columns(c, d_cols, col_stride, 0, n_cols, coeff_pitch, log_n, rate_bits, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch,
                     c->scratch.p, coeff_pitch, G, true, true, &sc, first_coset);
     }
+    for (int b = 0; b < 2; b++)              // join the shipments: the LDE stage ends when the last coset has left
+        if (c->sent_pending[b]) { CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_sent[b], 0)); c->sent_pending[b] = false; }
     record(c, GL_STAGE_LEAF_HASH);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->trace && c->trace_ev.size() > 1) {
+        cudaStreamSynchronize(c->send_stream);
+        fprintf(stderr, "[gl trace dev %d] coset: ntt start-end | send start-end (ms)\n", c->device);
+        for (size_t i = 1; i + 3 < c->trace_ev.size(); i += 4) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], c->trace_ev[0], c->trace_ev[i + j]);
+            fprintf(stderr, "[gl trace dev %d] %2zu: %7.3f-%7.3f | %7.3f-%7.3f\n", c->device, (i - 1) / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : c->trace_ev) cudaEventDestroy(e);
+        c->trace_ev.clear();
+    }
     for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE})
         if (host_cols || i != GL_STAGE_H2D) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     return GL_OK;
@@ -706,6 +802,7 @@ int gl_dev_ipc_alloc(gl_ctx* c, uint64_t words, uint64_t** out_ptr, uint8_t out_
     if (e != cudaSuccess) { cudaFree(p); CUDA_CHECK(e); }
     memcpy(out_handle, &h, 64);
     *out_ptr = p;
+    c->own_ipc.insert(p);
     return GL_OK;
     GL_API_END(c)
 }
@@ -730,6 +827,7 @@ int gl_dev_ipc_close(gl_ctx* c, uint64_t* ptr) {
 int gl_dev_ipc_free(gl_ctx* c, uint64_t* ptr) {
     GL_API_BEGIN(c)
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->own_ipc.erase(ptr);
     if (ptr) CUDA_CHECK(cudaFree(ptr));
     return GL_OK;
     GL_API_END(c)
