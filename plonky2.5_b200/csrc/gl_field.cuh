@@ -42,27 +42,7 @@ __device__ __forceinline__ uint64_t reduce_words(uint32_t z0, uint32_t z1, uint3
         "}" : "=&r"(l), "=&r"(h) : "r"(z0), "r"(z1), "r"(z2), "r"(z3));
     return ((uint64_t)h << 32) | l;
 }
-// Variant (compile with -DGL_REDUCE_MADWIDE): "+ z2*(2^32-1)" as one IMAD.WIDE (operand read from constant memory so
-// that ptxas does not strength-reduce it), carry seen as Yhi < Xhi.  3 fewer alu-pipe instructions, 1 more on fma-heavy.
-__constant__ uint32_t EPS_OPAQUE = 0xFFFFFFFFu;
-__device__ __forceinline__ uint64_t reduce_words_madwide(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3) {
-    uint32_t l, h;
-    asm("{\n\t.reg .u64 X, Y;\n\t.reg .u32 yl, yh, d, ds;\n\t.reg .pred p;\n\t"
-        "mov.b64      X, {%2, %3};\n\t"
-        "mad.wide.u32 Y, %4, %6, X;\n\t"
-        "mov.b64      {yl, yh}, Y;\n\t"
-        "setp.lt.u32  p, yh, %3;\n\t"
-        "sub.cc.u32   %0, yl, %5;\n\t"
-        "subc.cc.u32  %1, yh, 0;\n\t"
-        "subc.u32     d, 0, 0;\n\t"
-        "@p add.u32   d, d, 1;\n\t"
-        "shr.s32      ds, d, 31;\n\t"
-        "sub.cc.u32   %0, %0, d;\n\t"
-        "subc.u32     %1, %1, ds;\n\t"
-        "add.u32      %1, %1, d;\n\t"
-        "}" : "=&r"(l), "=&r"(h) : "r"(z0), "r"(z1), "r"(z2), "r"(z3), "r"(EPS_OPAQUE));
-    return ((uint64_t)h << 32) | l;
-}
+// (A variant that forms "+ z2*(2^32-1)" with one IMAD.WIDE — 3 fewer alu instructions, 1 more on the fma pipe — measured slower.)
 __device__ __forceinline__ uint64_t reduce128(uint64_t lo, uint64_t hi) {
     return reduce_words((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
@@ -106,11 +86,7 @@ __device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
 #else
     mul_words(a, b, z0, z1, z2, z3);
 #endif
-#ifdef GL_REDUCE_MADWIDE
-    return reduce_words_madwide(z0, z1, z2, z3);
-#else
     return reduce_words(z0, z1, z2, z3);
-#endif
 }
 // a^2: the cross product a0*a1 is computed once and added twice (3 IMAD.WIDE.U32 instead of 4)
 __device__ __forceinline__ uint64_t sqr(uint64_t a) {
@@ -129,11 +105,7 @@ __device__ __forceinline__ uint64_t sqr(uint64_t a) {
         "addc.cc.u32 %2, %2, m1;\n\t"
         "addc.u32    %3, %3, 0;\n\t"
         "}" : "=&r"(z0), "=&r"(z1), "=&r"(z2), "=&r"(z3) : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)));
-#ifdef GL_REDUCE_MADWIDE
-    return reduce_words_madwide(z0, z1, z2, z3);
-#else
     return reduce_words(z0, z1, z2, z3);
-#endif
 }
 __device__ __forceinline__ uint64_t mulc(uint64_t a, uint64_t b) { return canon(mul(a, b)); }
 

@@ -47,16 +47,6 @@ __device__ __forceinline__ void sbox_mul_words(uint64_t a, uint64_t b, uint32_t&
     else gl::mul_words(a, b, z0, z1, z2, z3);
 }
 
-__device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-    const uint64_t x2 = sbox_sqr<(POSEIDON_SBOX_FORM >> 0) & 1>(x);
-    const uint64_t x4 = sbox_sqr<(POSEIDON_SBOX_FORM >> 1) & 1>(x2);
-    uint32_t z0, z1, z2, z3;
-    sbox_mul_words<(POSEIDON_SBOX_FORM >> 2) & 1>(x, x2, z0, z1, z2, z3);
-    const uint64_t x3 = gl::reduce_words(z0, z1, z2, z3);
-    sbox_mul_words<(POSEIDON_SBOX_FORM >> 3) & 1>(x3, x4, z0, z1, z2, z3);
-    return gl::reduce_words(z0, z1, z2, z3);
-}
-
 constexpr double TWO52 = 4503599627370496.0;
 
 // {w, 0x43300000} is the double 2^52 + w
@@ -182,102 +172,12 @@ __device__ __forceinline__ void full_round(uint64_t (&s)[WIDTH], int r) {
 
 // ---- partial rounds: lanes 1..11 never leave the fp64 pipe ----------------------------------------------------------
 // Only lane 0 goes through the S-box in a partial round, so lanes 1..11 stay as (lo, hi) limb doubles — exact, signed,
-// un-reduced — from round 4 to round 25.  A layer multiplies magnitudes by <= 272, so limbs are renormalised every
-// second round (2^32.1 -> 2^40.2 -> 2^48.3 < 2^53).  The constants of those rounds are pushed forward through the MDS
-// so that only lane 0 receives one per round (tools/mds_model.py · partial_constants); lane 0's sums carry 2^52 plus an
-// offset = 0 (mod p) that keeps them positive, and are read back from the mantissa as before.
+// un-reduced — from round 4 to round 25.  The constants of those rounds are pushed forward through the MDS so that only
+// lane 0 receives one per round (tools/mds_model.py · partial_constants); lane 0's read-out carries 2^52 plus an offset
+// = 0 (mod p) that keeps it positive, and is read back from the mantissa.  (The first version of this idea kept the lanes
+// in the time domain, 89 fp64 operations per limb and round: tools/mds_model.py · permute_v3.)
 
-// mds_limb with the only non-zero folded constants uu0 = uv0 = q, v0 = 2q (lane-0 constant 4q)
-__device__ __forceinline__ void mds_limb_partial(const double (&s)[WIDTH], const double q, double (&o)[WIDTH]) {
-    double sp[6], sm[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        sp[i] = __dadd_rn(s[i], s[i + 6]);
-        sm[i] = __dsub_rn(s[i], s[i + 6]);
-    }
-    double a[3], b[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        a[i] = __dadd_rn(sp[i], sp[i + 3]);
-        b[i] = __dsub_rn(sp[i], sp[i + 3]);
-    }
-    const double S16 = __dmul_rn(__dadd_rn(__dadd_rn(a[0], a[1]), a[2]), 16.0);
-    double U[6], V[6];
-    {
-        double UU[3], UV[3];
-        UU[0] = __fma_rn(a[2], 16.0, __dadd_rn(S16, q));
-        UU[1] = __fma_rn(a[0], 16.0, S16);
-        UU[2] = __fma_rn(a[1], 16.0, S16);
-        UV[0] = __fma_rn(b[2], 8.0, __fma_rn(b[1], -2.0, __dsub_rn(q, b[0])));
-        UV[1] = __fma_rn(b[2], -2.0, __fma_rn(b[0], -8.0, -b[1]));
-        UV[2] = __fma_rn(b[1], -8.0, __fma_rn(b[0], 2.0, -b[2]));
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            U[j] = __dadd_rn(UU[j], UV[j]);
-            U[j + 3] = __dsub_rn(UU[j], UV[j]);
-        }
-    }
-    // negacyclic-6 rows, coefficient of sm[j] in V[n] is f[n-j] (j <= n) or -f[6+n-j]; f = [2,-4,16,1,-1,-1]
-    V[0] = __fma_rn(sm[0], 2.0, __fma_rn(sm[4], -16.0, __fma_rn(sm[5], 4.0, __dadd_rn(__dadd_rn(sm[1], sm[2]), __fma_rn(q, 2.0, -sm[3])))));
-    V[1] = __fma_rn(sm[0], -4.0, __fma_rn(sm[1], 2.0, __fma_rn(sm[5], -16.0, __dsub_rn(__dadd_rn(sm[2], sm[3]), sm[4]))));
-    V[2] = __fma_rn(sm[0], 16.0, __fma_rn(sm[1], -4.0, __fma_rn(sm[2], 2.0, __dsub_rn(__dadd_rn(sm[3], sm[4]), sm[5]))));
-    V[3] = __fma_rn(sm[1], 16.0, __fma_rn(sm[2], -4.0, __fma_rn(sm[3], 2.0, __dadd_rn(__dadd_rn(sm[0], sm[4]), sm[5]))));
-    V[4] = __fma_rn(sm[2], 16.0, __fma_rn(sm[3], -4.0, __fma_rn(sm[4], 2.0, __dadd_rn(__dsub_rn(sm[1], sm[0]), sm[5]))));
-    V[5] = __fma_rn(sm[3], 16.0, __fma_rn(sm[4], -4.0, __fma_rn(sm[5], 2.0, __dsub_rn(__dsub_rn(sm[2], sm[0]), sm[1]))));
-    U[0] = __fma_rn(s[0], 4.0, U[0]);
-    V[0] = __fma_rn(s[0], 4.0, V[0]);
-#pragma unroll
-    for (int n = 0; n < 6; n++) {
-        o[n] = __dadd_rn(U[n], V[n]);
-        o[n + 6] = __dsub_rn(U[n], V[n]);
-    }
-}
-
-// (L, H) with value L + H*2^32 -> same value mod p with |L|, |H| <= 2^31 + 2^17  (inputs up to 2^49)
-__device__ __forceinline__ void normalize_limbs(double& L, double& H) {
-    constexpr double MAGIC = 6755399441055744.0;     // 1.5 * 2^52: adding it rounds to an integer
-    constexpr double INV32 = 2.3283064365386963e-10;  // 2^-32
-    constexpr double B32 = 4294967296.0;
-    const double cL = __dsub_rn(__fma_rn(L, INV32, MAGIC), MAGIC);
-    L = __fma_rn(cL, -B32, L);
-    H = __dadd_rn(H, cL);
-    const double cH = __dsub_rn(__fma_rn(H, INV32, MAGIC), MAGIC);   // cH * 2^64 = cH * (2^32 - 1)
-    H = __fma_rn(cH, -(B32 - 1.0), H);                               // H - cH*2^32 + cH, one exact operation
-    L = __dsub_rn(L, cH);
-}
-
-#if defined(POSEIDON_PARTIAL_V3)
-__device__ __forceinline__ void partial_rounds(uint64_t (&s)[WIDTH]) {
-    double L[WIDTH], H[WIDTH];
-#pragma unroll
-    for (int i = 1; i < WIDTH; i++) {
-        L[i] = limb_to_double((uint32_t)s[i]);
-        H[i] = limb_to_double((uint32_t)(s[i] >> 32));
-    }
-    uint64_t x0 = s[0];
-#pragma unroll 1
-    for (int r = N_FULL_HALF; r < N_FULL_HALF + N_PARTIAL; r++) {
-        sbox7_limbs(x0, L[0], H[0]);
-        double OL[WIDTH], OH[WIDTH];
-        mds_limb_partial(L, POSEIDON_PARTIAL_Q[r - N_FULL_HALF][0], OL);
-        mds_limb_partial(H, POSEIDON_PARTIAL_Q[r - N_FULL_HALF][1], OH);
-        x0 = recombine(OL[0], OH[0]);
-#pragma unroll
-        for (int i = 1; i < WIDTH; i++) {
-            L[i] = OL[i];
-            H[i] = OH[i];
-        }
-        if (r & 1) {
-#pragma unroll
-            for (int i = 1; i < WIDTH; i++) normalize_limbs(L[i], H[i]);
-        }
-    }
-    s[0] = x0;
-#pragma unroll
-    for (int i = 1; i < WIDTH; i++)
-        s[i] = recombine(__dadd_rn(L[i], POSEIDON_PARTIAL_TAIL[i - 1][0]), __dadd_rn(H[i], POSEIDON_PARTIAL_TAIL[i - 1][1]));
-}
-#elif defined(POSEIDON_PARTIAL_V4)
+#if defined(POSEIDON_PARTIAL_V4)
 // ---- v4: the 11 resident lanes live in the CRT domain of the circulant ------------------------------------------------
 // With a_i, b_i, m_i as in mds_limb (cyclic-3, negacyclic-3, negacyclic-6 parts of one limb vector) the MDS layer acts
 // blockwise, a' = 4*UU(a), b' = 4*UV(b), m' = 2*V(m): the 30 add/sub butterflies of the time-domain layer disappear

@@ -14,6 +14,7 @@ torch.distributed is plumbing only: the exchange is `all_to_all_single` on devic
 from __future__ import annotations
 
 import ctypes
+import time
 from typing import List, Tuple
 
 import numpy as np
@@ -88,11 +89,12 @@ def exchange_reference(plan: ShardPlan, shards: List[np.ndarray]) -> List[np.nda
 class ShardedCommit:
     """Device buffers + the four steps above for one rank.  Buffers are allocated once and reused by every commit.
 
-    exchange="p2p" (default when the ranks can map each other's memory): steps 1 and 2 are ONE kernel sequence — the last
-    NTT pass of every coset stores each 64-byte leaf-row segment straight into the owner's leaf buffer over NVLink
-    (gl_dev_lde_scatter; buffers exported/mapped with CUDA IPC), so there is no all-to-all, no receive buffer and no
-    repacking; the ranks only meet at a barrier before hashing.  exchange="nccl": gl_dev_lde + all_to_all_single +
-    gl_dev_repack (the baseline the fused path is measured against)."""
+    exchange="p2p" (default when the ranks can map each other's memory): steps 1 and 2 are one call — gl_dev_lde_scatter /
+    gl_lde_scatter deliver every coset's rows into the owners' leaf buffers over NVLink (buffers exported/mapped with CUDA IPC)
+    while the next coset's NTT runs (copy engines by default, NTT-side remote stores or a copy kernel with
+    GL_SCATTER_MODE), so there is no all-to-all, no receive buffer and no repacking; the ranks only meet at a stream-ordered
+    1-element all-reduce before hashing.  exchange="nccl": gl_dev_lde + all_to_all_single + gl_dev_repack (the baseline the
+    fused path is measured against, and the collective fallback when peer mapping is unavailable)."""
 
     def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch, exchange: str = "p2p"):
         self.ctx, self.plan, self.rank, self.dist, self.torch = ctx, plan, rank, dist, torch
@@ -186,7 +188,6 @@ class ShardedCommit:
         n = 1 << p.log_n
         ncg = p.col_counts[self.rank]
         assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
-        import time
         t0 = time.perf_counter()
         if self.exchange == "p2p":
             # Nobody may write into a leaf buffer its owner is still hashing: the previous commit ended with the cap
@@ -242,7 +243,6 @@ class ShardedCommit:
 
     def _hash(self) -> np.ndarray:
         p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
-        import time
         t0 = time.perf_counter()
         self._check(lib.gl_dev_merkle(h, self.leaves_ptr, p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
                                       self.digests.data_ptr(), self.cap_local.ctypes.data))

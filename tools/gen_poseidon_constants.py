@@ -80,22 +80,8 @@ def mds_tables(rc):
     for row in rows:
         txt += "    {" + ", ".join("%d.0" % v for v in row) + "},\n"
     txt += "};\n"
-    # partial rounds with lanes 1..11 resident in fp64 (mds_model.permute_v3): only lane 0 receives a constant
-    from mds_model import partial_constants, BIAS, OFF_LO, OFF_HI
+    from mds_model import partial_constants, BIAS
     lane0, tail = partial_constants(rc)
-    txt += ("// PARTIAL_Q[r-4][limb] = (limb of the pushed-forward lane-0 constant of round r+1 + 2^52 + positivity offset) / 4\n"
-            "__constant__ double POSEIDON_PARTIAL_Q[22][2] = {\n")
-    for r in range(4, 26):
-        cl, ch = rc_limbs(lane0[r + 1])
-        ql, qh = cl + BIAS + OFF_LO, ch + BIAS + OFF_HI
-        assert ql % 4 == 0 and qh % 4 == 0
-        txt += "    {%d.0, %d.0},\n" % (ql // 4, qh // 4)
-    txt += ("};\n// PARTIAL_TAIL[i-1][limb]: what lane i (1..11) receives when it leaves the fp64 domain before round 26: pushed-forward\n"
-            "// constant limb + positivity offset + 2^52\n__constant__ double POSEIDON_PARTIAL_TAIL[11][2] = {\n")
-    for i in range(11):
-        cl, ch = rc_limbs(tail[i])
-        txt += "    {%d.0, %d.0},\n" % (cl + OFF_LO + BIAS, ch + OFF_HI + BIAS)
-    txt += "};\n"
     # v4: partial rounds in the CRT domain of the circulant (mds_model.permute_v4): the constant is added at read-out
     from mds_model import OFF4_LO, OFF4_HI
     txt += ("// PARTIAL4_Q[r-4][limb] = limb of the pushed-forward lane-0 constant of round r+1 + 2^52 + positivity offset (2^19 p split)\n"
@@ -104,7 +90,8 @@ def mds_tables(rc):
         cl, ch = rc_limbs(lane0[r + 1])
         assert 0 <= cl + OFF4_LO < BIAS and 0 <= ch + OFF4_HI < BIAS
         txt += "    {%d.0, %d.0},\n" % (cl + BIAS + OFF4_LO, ch + BIAS + OFF4_HI)
-    txt += "};\n// PARTIAL4_TAIL[i-1][limb]: as PARTIAL_TAIL with the v4 offsets\n__constant__ double POSEIDON_PARTIAL4_TAIL[11][2] = {\n"
+    txt += ("};\n// PARTIAL4_TAIL[i-1][limb]: what lane i (1..11) receives when it leaves the fp64 domain before round 26: pushed-forward\n"
+            "// constant limb + positivity offset + 2^52\n__constant__ double POSEIDON_PARTIAL4_TAIL[11][2] = {\n")
     for i in range(11):
         cl, ch = rc_limbs(tail[i])
         txt += "    {%d.0, %d.0},\n" % (cl + OFF4_LO + BIAS, ch + OFF4_HI + BIAS)
