@@ -86,6 +86,10 @@ int gl_tree_info(gl_ctx* ctx, gl_handle tree, gl_tree_info_t* out);
 int gl_tree_get(gl_ctx* ctx, gl_handle tree, uint64_t leaf_index, uint64_t* out_row /* leaf_len */);
 /* siblings bottom-up, (log2(n_leaves) - cap_height) * 4 words — MerkleProof::siblings */
 int gl_tree_prove(gl_ctx* ctx, gl_handle tree, uint64_t leaf_index, uint64_t* out_siblings);
+/* gl_tree_get + gl_tree_prove for n leaf indices in one launch and two copies (the FRI query rounds open 28 indices in every
+ * tree): out_rows = [n][leaf_len], out_siblings = [n][log2(n_leaves) - cap_height][4]; either may be NULL                     */
+int gl_tree_open_batch(gl_ctx* ctx, gl_handle tree, const uint64_t* leaf_indices, uint32_t n, uint64_t* out_rows,
+                       uint64_t* out_siblings);
 /* leaves[bitrev(index * step)] — PolynomialBatch::get_lde_values */
 int gl_tree_get_lde_values(gl_ctx* ctx, gl_handle tree, uint64_t index, uint64_t step, uint64_t* out_row);
 enum { GL_PART_COEFFS = 0, GL_PART_LEAVES = 1, GL_PART_DIGESTS = 2, GL_PART_CAP = 3 };

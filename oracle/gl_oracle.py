@@ -605,3 +605,22 @@ def prove_openings_lde(final_poly: Sequence[Ext], rate_bits: int):
     """lde_final_poly = final_poly.lde(rate_bits); lde_final_values = lde_final_poly.coset_fft(7)"""
     lde = list(final_poly) + [(0, 0)] * (len(final_poly) * ((1 << rate_bits) - 1))
     return lde, ext_coset_fft(lde, MULTIPLICATIVE_GROUP_GENERATOR)
+
+
+def fri_prover_query_rounds(initial_trees: Sequence[MerkleTree], trees: Sequence[MerkleTree], challenger: Challenger,
+                            n_query_rounds: int, reduction_arity_bits: Sequence[int], lde_size: int):
+    """plonky2/src/fri/prover.rs · fri_prover_query_rounds / fri_prover_query_round (restated from memory of upstream @ 3de92d9)."""
+    rounds = []
+    for _ in range(n_query_rounds):
+        x_index = challenger.get_challenge() % lde_size
+        rnd = {"x_index": x_index, "initial_trees_proof": [(t.get(x_index), t.prove(x_index)) for t in initial_trees], "steps": []}
+        x = x_index
+        for arity_bits, tree in zip(reduction_arity_bits, trees):
+            arity = 1 << arity_bits
+            flat = tree.get(x >> arity_bits)
+            evals = [(flat[2 * i], flat[2 * i + 1]) for i in range(arity)]
+            del evals[x & (arity - 1)]
+            rnd["steps"].append({"evals": evals, "merkle_proof": tree.prove(x >> arity_bits)})
+            x >>= arity_bits
+        rounds.append(rnd)
+    return rounds

@@ -37,6 +37,7 @@ SIGNATURES = {
     "gl_tree_info": (c_int, [c_void_p, c_uint64, POINTER(TreeInfo)]),
     "gl_tree_get": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p]),
     "gl_tree_prove": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p]),
+    "gl_tree_open_batch": (c_int, [c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p]),
     "gl_tree_get_lde_values": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, c_void_p]),
     "gl_tree_read": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
     "gl_tree_free": (c_int, [c_void_p, c_uint64]),

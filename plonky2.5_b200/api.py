@@ -180,6 +180,16 @@ class MerkleTree:
         _check(self.ctx, self.ctx.lib.gl_tree_prove(self.ctx.handle, self._h, leaf_index, _ptr(out)))
         return out
 
+    def open_batch(self, indices) -> Tuple[np.ndarray, np.ndarray]:
+        """(get(i), prove(i)) for every i of `indices` in one device round trip: ([n][leaf_len], [n][depth][4])."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).reshape(-1)
+        depth = self.n_leaves.bit_length() - 1 - self.cap_height
+        rows = np.zeros((idx.size, self.leaf_len), dtype=np.uint64)
+        sib = np.zeros((idx.size, depth, 4), dtype=np.uint64)
+        _check(self.ctx, self.ctx.lib.gl_tree_open_batch(self.ctx.handle, self._h, _ptr(idx) if idx.size else None, idx.size,
+                                                         _ptr(rows), _ptr(sib)))
+        return rows, sib
+
     def free(self):
         if self._h and self.ctx.handle:
             self.ctx.lib.gl_tree_free(self.ctx.handle, self._h)
@@ -451,3 +461,31 @@ def prove_openings(instance: Sequence[FriBatchInfo], oracles: Sequence["Polynomi
         lib.gl_fri_end(ctx.handle, fh.value)
     w = fri_proof_of_work(challenger, proof_of_work_bits, ctx) if proof_of_work_bits is not None else None
     return FriProofHead(trees, final, w, int(n.value))
+
+
+def fri_prover_query_rounds(initial_merkle_trees: Sequence[MerkleTree], trees: Sequence[MerkleTree], challenger, n_query_rounds: int,
+                            fri_params: FriParams, lde_size: Optional[int] = None) -> List[dict]:
+    """plonky2 fri/prover.rs · fri_prover_query_rounds / fri_prover_query_round: per round x_index = challenge mod lde_size;
+    initial_trees_proof = [(tree.get(x), tree.prove(x))] for every initial oracle; per commit-phase layer the coset evaluations
+    (the leaf x >> arity_bits with the queried element removed) and the Merkle proof of that leaf.  All indices of a tree are
+    opened in one gl_tree_open_batch call.  Returns one dict per round:
+    {"x_index", "initial_trees_proof": [(row, siblings)], "steps": [{"evals": [arity-1][2], "merkle_proof": siblings}]}."""
+    n = int(lde_size if lde_size is not None else initial_merkle_trees[0].n_leaves)
+    xs = [int(challenger.get_challenge()) % n for _ in range(n_query_rounds)]
+    init = [t.open_batch(xs) for t in initial_merkle_trees]
+    steps = []
+    cur = list(xs)
+    for arity_bits, t in zip(fri_params.reduction_arity_bits, trees):
+        rows, sib = t.open_batch([x >> arity_bits for x in cur])
+        steps.append((arity_bits, rows, sib, list(cur)))
+        cur = [x >> arity_bits for x in cur]
+    out = []
+    for q, x in enumerate(xs):
+        rnd = {"x_index": x, "initial_trees_proof": [(rows[q], sib[q]) for rows, sib in init], "steps": []}
+        for arity_bits, rows, sib, idx in steps:
+            evals = rows[q].reshape(-1, 2)
+            keep = np.ones(1 << arity_bits, dtype=bool)
+            keep[idx[q] & ((1 << arity_bits) - 1)] = False        # evals.remove(x_index & (arity - 1))
+            rnd["steps"].append({"evals": evals[keep], "merkle_proof": sib[q]})
+        out.append(rnd)
+    return out

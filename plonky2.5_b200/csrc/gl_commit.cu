@@ -950,6 +950,33 @@ int gl_tree_prove(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_sib
     GL_API_END(c)
 }
 
+int gl_tree_open_batch(gl_ctx* c, gl_handle h, const uint64_t* leaf_indices, uint32_t n, uint64_t* out_rows, uint64_t* out_siblings) {
+    GL_API_BEGIN(c)
+    Tree* t = find_tree(c, h);
+    if (n == 0) return GL_OK;
+    if (!leaf_indices) GL_THROW(GL_ERR_INVALID, "leaf_indices is NULL");
+    for (uint32_t q = 0; q < n; q++)
+        if (leaf_indices[q] >= t->n_leaves) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
+    const uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
+    const size_t row_words = (size_t)n * t->leaf_len, sib_words = (size_t)n * log_sub * 4;
+    c->scratch.ensure(n + row_words + sib_words + 1);
+    uint64_t* d_idx = c->scratch.p;
+    uint64_t* d_rows = d_idx + n;
+    uint64_t* d_sib = d_rows + row_words;
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, leaf_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t total = (uint64_t)n * (t->leaf_len + 4 * log_sub);
+    if (total) {
+        merkle::open_batch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(t->leaves.p, t->pitch, t->leaf_len, t->digests.p,
+                                                                                        log_sub, d_idx, n, d_rows, d_sib);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    if (out_rows && row_words) CUDA_CHECK(cudaMemcpyAsync(out_rows, d_rows, 8 * row_words, cudaMemcpyDeviceToHost, c->stream));
+    if (out_siblings && sib_words) CUDA_CHECK(cudaMemcpyAsync(out_siblings, d_sib, 8 * sib_words, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
 int gl_tree_read(gl_ctx* c, gl_handle h, int part, uint64_t* out) {
     GL_API_BEGIN(c)
     Tree* t = find_tree(c, h);

@@ -83,6 +83,25 @@ tree_level_kernel(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, ui
     store_digest(dst, s);
 }
 
+// FRI query rounds (plonky2 fri/prover.rs · fri_prover_query_round): MerkleTree::get + MerkleTree::prove for a batch of leaf
+// indices in one launch.  Thread (q, w): word w of the answer for query q — first the leaf row, then depth*4 sibling words.
+__global__ void open_batch_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t leaf_len, const uint64_t* __restrict__ digests,
+                                  uint32_t log_sub, const uint64_t* __restrict__ indices, uint32_t n_queries,
+                                  uint64_t* __restrict__ out_rows, uint64_t* __restrict__ out_siblings) {
+    const uint32_t per_q = leaf_len + 4 * log_sub;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)n_queries * per_q) return;
+    const uint32_t q = (uint32_t)(i / per_q), w = (uint32_t)(i % per_q);
+    const uint64_t leaf = indices[q];
+    if (w < leaf_len) {
+        out_rows[(size_t)q * leaf_len + w] = leaves[leaf * pitch + w];
+        return;
+    }
+    const uint32_t layer = (w - leaf_len) >> 2, k = (w - leaf_len) & 3;
+    const uint64_t L = 1ULL << log_sub, sub = leaf >> log_sub, j = (leaf & (L - 1)) >> layer;
+    out_siblings[((size_t)q * log_sub + layer) * 4 + k] = digests[4 * (sub * 2 * (L - 1) + digest_index(layer, j ^ 1)) + k];
+}
+
 // Batch of independent permutations (host challenger / PoW plumbing): states[n][12] in place, canonical out.
 __global__ void permute_kernel(uint64_t* __restrict__ states, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -331,3 +331,51 @@ def test_prove_openings_errors(ctx):
         g.prove_openings([g.FriBatchInfo((1, 2), [(0, 0), (1, 0)])], [a, b], ch, g.FriParams(1, 1, []), ctx=ctx)
     with pytest.raises(ValueError, match="out of range"):
         g.prove_openings([g.FriBatchInfo((1, 2), [(0, 3)])], [a], ch, g.FriParams(1, 1, []), ctx=ctx)
+
+
+@pytest.mark.parametrize("cfg", [(6, [9, 5], 2, 2, [2, 2], 5), (10, [135, 20], 3, 4, [4, 4], 28), (4, [3], 1, 5, [], 3)])
+def test_fri_query_rounds_open_and_verify(ctx, oc, cfg):
+    """prove_openings -> fri_prover_query_rounds: every opened row equals the single-call readers (already checked against the
+    oracle), every Merkle path verifies with the VERIFIER's rule against the committed cap, the commit-phase evaluations are the
+    layer leaves with the queried element removed (the structure oracle/gl_oracle.py · fri_prover_query_rounds restates)."""
+    g = _g()
+    log_n, widths, r, cap_h, arities, n_rounds = cfg
+    n = 1 << log_n
+    cols = [splitmix_columns(300 + 13 * k + log_n, w, n) for k, w in enumerate(widths)]
+    cap_h = min(cap_h, log_n + r)
+    batches = [g.PolynomialBatch.from_values(list(c), r, False, cap_h, ctx=ctx) for c in cols]
+    instance = [g.FriBatchInfo((11, 22), [(k, i) for k, w in enumerate(widths) for i in range(w)])]
+    ch = g.Challenger(ctx)
+    ch.observe_elements([1, 2, 3])
+    head = g.prove_openings(instance, batches, ch, g.FriParams(r, cap_h, arities), proof_of_work_bits=4, ctx=ctx)
+    ch2 = g.Challenger(ctx)                      # the query indices come from the transcript: replay them for the checker
+    ch2.sponge_state, ch2.input_buffer, ch2.output_buffer = ch.sponge_state.copy(), list(ch.input_buffer), list(ch.output_buffer)
+    rounds = g.fri_prover_query_rounds([b.merkle_tree for b in batches], head.trees, ch, n_rounds, g.FriParams(r, cap_h, arities))
+    assert len(rounds) == n_rounds
+    for rnd in rounds:
+        x = int(ch2.get_challenge()) % (n << r)
+        assert rnd["x_index"] == x
+        for b, (row, sib) in zip(batches, rnd["initial_trees_proof"]):
+            t = b.merkle_tree
+            assert np.array_equal(row, t.get(x)) and np.array_equal(sib, t.prove(x))
+            assert oc.verify_path(row, x, sib, t.cap.hashes)
+        for arity_bits, t, step in zip(arities, head.trees, rnd["steps"]):
+            leaf = t.get(x >> arity_bits)
+            ev = leaf.reshape(-1, 2)
+            keep = [i for i in range(1 << arity_bits) if i != (x & ((1 << arity_bits) - 1))]
+            assert np.array_equal(step["evals"], ev[keep])
+            assert np.array_equal(step["merkle_proof"], t.prove(x >> arity_bits))
+            assert oc.verify_path(leaf, x >> arity_bits, step["merkle_proof"], t.cap.hashes)
+            x >>= arity_bits
+
+
+def test_tree_open_batch_edges(ctx):
+    g = _g()
+    lv = splitmix_columns(9, 8, 5)                       # 8 leaves of 5 words
+    t = g.MerkleTree.new(lv, 3, ctx=ctx)                 # cap_height = log2(n_leaves): no digests, empty proofs
+    rows, sib = t.open_batch([7, 0, 7])
+    assert np.array_equal(rows, lv[[7, 0, 7]]) and sib.shape == (3, 0, 4)
+    rows, sib = t.open_batch([])
+    assert rows.shape == (0, 5)
+    with pytest.raises(ValueError, match="out of range"):
+        t.open_batch([8])

@@ -307,3 +307,32 @@ def test_openings_front_half_identities(case):
     x = o.MULTIPLICATIVE_GROUP_GENERATOR * pow(o.primitive_root_of_unity(o.log2_strict(len(lde))), 3, o.P) % o.P if len(lde) > 4 else None
     if x is not None:
         assert vals[3] == o.ext_eval_poly(final, x)
+
+
+def test_fri_query_rounds_restatement_verifies():
+    """oracle-only: prove_openings front half -> fri_committed_trees -> fri_prover_query_rounds; every opened path verifies with the
+    verifier's rule and the commit-phase evaluations re-assemble the committed leaf."""
+    log_n, r, cap_h, arities = 4, 2, 2, [2, 2]
+    n = 1 << log_n
+    cols = [[int(v) for v in c] for c in splitmix_columns(55, 5, n)]
+    batch = o.PolynomialBatch.from_values(cols, r, cap_h)
+    ch = o.Challenger()
+    ch.observe_elements([4, 5, 6])
+    alpha = ch.get_extension_challenge()
+    final, _ = o.prove_openings_final_poly([((3, 9), [(0, i) for i in range(5)])], [batch.polynomials], alpha)
+    lde, vals = o.prove_openings_lde(final, r)
+    trees, final_poly = o.fri_committed_trees(lde, vals, ch, arities, r, cap_h)
+    o.fri_proof_of_work(ch, 3)
+    rounds = o.fri_prover_query_rounds([batch.merkle_tree], trees, ch, 6, arities, n << r)
+    assert len(rounds) == 6
+    for rnd in rounds:
+        x = rnd["x_index"]
+        row, proof = rnd["initial_trees_proof"][0]
+        assert o.verify_merkle_proof_to_cap(row, x, batch.merkle_tree.cap, proof)
+        for arity_bits, tree, step in zip(arities, trees, rnd["steps"]):
+            leaf = tree.get(x >> arity_bits)
+            evals = list(step["evals"])
+            evals.insert(x & ((1 << arity_bits) - 1), (leaf[2 * (x & ((1 << arity_bits) - 1))], leaf[2 * (x & ((1 << arity_bits) - 1)) + 1]))
+            assert [w for e in evals for w in e] == list(leaf)
+            assert o.verify_merkle_proof_to_cap(leaf, x >> arity_bits, tree.cap, step["merkle_proof"])
+            x >>= arity_bits
