@@ -164,6 +164,7 @@ struct gl_ctx {
     std::mutex mu;
     std::string err;
     std::map<uint32_t, std::unique_ptr<DevBuf>> roots;                       // log_n -> W
+    std::map<uint32_t, std::unique_ptr<DevBuf>> pass_roots;                  // a -> w_{2^a}^e, e < 7*2^a/8 (round twiddles)
     std::map<uint64_t, std::unique_ptr<std::vector<CosetTable>>> lde_tables;  // (log_n, rate_bits) -> per coset
     DevBuf in_stage, vals, scratch;
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
@@ -209,6 +210,25 @@ const uint64_t* get_roots(gl_ctx* c, uint32_t log_n) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     const uint64_t* p = buf->p;
     c->roots[log_n] = std::move(buf);
+    return p;
+}
+
+const uint64_t* get_pass_roots(gl_ctx* c, uint32_t a) {
+    auto it = c->pass_roots.find(a);
+    if (it != c->pass_roots.end()) return it->second->p;
+    const size_t T = (size_t)1 << a, n = T - (T >> 3);
+    std::vector<uint64_t> w(n ? n : 1);
+    uint64_t root = gl::h_root_of_unity(a), cur = 1;
+    for (size_t e = 0; e < n; e++) {
+        w[e] = e < (T >> 1) ? cur : gl::P - w[e - (T >> 1)];   // w_T^(e) = -w_T^(e - T/2); never 0, so P - x is canonical
+        cur = gl::h_mul(cur, root);
+    }
+    auto buf = std::make_unique<DevBuf>();
+    buf->ensure(w.size());
+    CUDA_CHECK(cudaMemcpyAsync(buf->p, w.data(), w.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const uint64_t* p = buf->p;
+    c->pass_roots[a] = std::move(buf);
     return p;
 }
 
@@ -300,6 +320,7 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
         p.log_blk = log_blk;
         p.a = passes[i];
         p.W = W;
+        p.Wa = get_pass_roots(c, passes[i]);
         p.pre = (first && pre) ? pre->F.p : nullptr;
         p.store_mode = (ifft && last) ? 1 : 0;
         p.scale = (ifft && last) ? n_inv : 1;
@@ -650,6 +671,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->fris.clear();
     c->openings.clear();
     c->roots.clear();
+    c->pass_roots.clear();
     c->lde_tables.clear();
     c->in_stage.release(); c->vals.release(); c->scratch.release();
     DevPool::get().trim(c->device);

@@ -32,6 +32,7 @@ struct PassParams {
     uint32_t a;                      // stages done in this pass (>= 3)
     uint32_t ncg;                    // column groups (pitch / G)
     const uint64_t* W;               // w_N^e, e < max(N/2, 1), canonical
+    const uint64_t* Wa;              // w_T^e, e < 7T/8 (T = 2^a), the upper eighths as -w_T^(e - T/2): round twiddles of this pass size
     const uint64_t* pre;             // coset pre-scale (first pass only): g^row, row < N, or nullptr
     uint32_t store_mode;             // 0: row p -> p ; 1: iFFT: row p -> (N - bitrev_n(p)) mod N ; 2: scatter to leaf owners
     uint64_t scale;                  // multiply at store when != 1 (1/N for the iFFT)
@@ -121,21 +122,23 @@ ntt_pass_kernel(const PassParams p) {   // >= 48 resident warps per SM where the
     const uint32_t row_base = (o_hi << p.log_blk) | o_lo;
     const uint32_t col = cg * G + c;
 
-    // Wl[e] = w_T^e for e < 7T/8 (radix-8 twiddle exponents reach 7 * (T/8 - 1)); the upper part is -w_T^(e - T/2)
-    for (uint32_t e = tid; e < T - (T >> 3); e += nthr)
-        Wl[e] = e < (T >> 1) ? p.W[(size_t)e << (p.log_n - a)] : gl::P - p.W[(size_t)(e - (T >> 1)) << (p.log_n - a)];
-
+    // The tile's own loads go first: they are strided gathers from HBM and everything below waits for them, so the
+    // round-twiddle staging (a contiguous, L2-resident table) and the pre-scale factors are fetched in their shadow.
     uint64_t x[8];
     uint32_t sh = a - 3;
-    {
-        const bool pre = p.pre != nullptr;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const uint64_t row = row_base | ((uint64_t)ins3(q, sh, e) << b_lo);
+        x[e] = p.src[row * p.src_pitch + col];
+    }
+    // Wl[e] = w_T^e for e < 7T/8 (radix-8 twiddle exponents reach 7 * (T/8 - 1); the upper part is -w_T^(e - T/2)):
+    // p.Wa is that table for this pass size, contiguous in global memory
+    for (uint32_t e = tid; e < T - (T >> 3); e += nthr) Wl[e] = __ldg(p.Wa + e);
+    if (p.pre != nullptr) {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            uint32_t l = ins3(q, sh, e);
-            uint64_t row = row_base | ((uint64_t)l << b_lo);
-            uint64_t v = p.src[row * p.src_pitch + col];
-            if (pre) v = gl::mul(v, __ldg(p.pre + row));
-            x[e] = v;
+            const uint64_t row = row_base | ((uint64_t)ins3(q, sh, e) << b_lo);
+            x[e] = gl::mul(x[e], __ldg(p.pre + row));
         }
     }
     __syncthreads();   // Wl ready
