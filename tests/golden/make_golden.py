@@ -9,6 +9,8 @@
                            src/p3/extension.rs:149,155, src/p3/serde/two_adic.rs:19,35,66).
 * derived_anchors.json   — values derived from the restated spec by the Python big-int oracle (NOT from an upstream
                            binary: "parity unpinned" for these, they are regression anchors shared with SURVEY.md C.3/C.4).
+* openings_fri.json      — prove_openings front half -> FRI commit phase -> PoW -> query indices on one seeded transcript
+                           (C oracle; regression anchor, parity unpinned).
 * commit_small.json      — seeded small commits (inputs by SplitMix64 seed, outputs: cap + sha256 of coeffs/leaves/digests)
                            produced by the C oracle after it was cross-checked against the Python oracle.
 """
@@ -66,6 +68,32 @@ def main():
                       "sha256_leaves": sha(res["leaves"]), "sha256_digests": sha(res["digests"])})
     json.dump({"generator": "oracle/gl_oracle.c via tests/golden/make_golden.py; inputs = tests/oracle_c.py splitmix_columns(seed)",
                "cases": cases}, open(os.path.join(HERE, "commit_small.json"), "w"), indent=1)
+    # prove_openings front half + FRI commit phase + PoW + query indices on one seeded transcript (regression anchor: derived
+    # from the restated spec by the C oracle after it was cross-checked against the Python oracle; parity unpinned)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u8").tobytes()).hexdigest()
+    log_n, widths, r, cap_h, arities, pow_bits = 8, [9, 5, 2], 3, 4, [4, 3], 6
+    cols = [splitmix_columns(40 + k, w, 1 << log_n) for k, w in enumerate(widths)]
+    coeffs = [oc.commit(c, r, cap_h)["coeffs"] for c in cols]
+    batches = [((123456789, 987654321), [(k, i) for k, w in enumerate(widths) for i in range(w)]), ((5, 0), [(2, 0), (2, 1)])]
+    ch = oc.new_challenger()
+    ch.observe_elements(list(range(1, 12)))
+    alpha = ch.get_extension_challenge()
+    final, quots = oc.openings_final_poly(batches, coeffs, alpha)
+    n = 1 << log_n
+    lde = np.zeros((n << r, 2), dtype=np.uint64)
+    lde[:n] = final
+    vals = np.stack([oc.coset_fft(lde[:, 0], 7), oc.coset_fft(lde[:, 1], 7)], axis=1)
+    fri = oc.fri_committed_trees(lde, vals, arities, r, cap_h, ch)
+    w = ch.fri_proof_of_work(pow_bits)
+    xs = [ch.get_challenge() % (n << r) for _ in range(4)]
+    json.dump({"generator": "oracle/gl_oracle.c via tests/golden/make_golden.py", "log_n": log_n, "widths": widths, "rate_bits": r,
+               "cap_height": cap_h, "arity_bits": arities, "pow_bits": pow_bits, "col_seeds": [40 + k for k in range(len(widths))],
+               "transcript_prefix": list(range(1, 12)),
+               "batches": [{"point": list(pt), "polynomials": [list(x) for x in polys]} for pt, polys in batches],
+               "alpha": [int(alpha[0]), int(alpha[1])], "sha256_final_poly": sha(final), "sha256_quotients": [sha(q) for q in quots],
+               "commit_phase_caps": [[int(x) for x in c.reshape(-1)] for c in fri["caps"]],
+               "fri_final_poly": [[int(a), int(b)] for a, b in fri["final_poly"]], "pow_witness": int(w), "query_indices": [int(x) for x in xs]},
+              open(os.path.join(HERE, "openings_fri.json"), "w"), indent=1)
     print("golden fixtures written")
 
 

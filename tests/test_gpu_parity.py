@@ -379,3 +379,26 @@ def test_tree_open_batch_edges(ctx):
     assert rows.shape == (0, 5)
     with pytest.raises(ValueError, match="out of range"):
         t.open_batch([8])
+
+
+def test_openings_fri_golden_fixture_on_gpu(ctx, golden):
+    """commits -> prove_openings -> query indices reproduce tests/golden/openings_fri.json on the device."""
+    g = _g()
+    f = golden["openings_fri"]
+    n = 1 << f["log_n"]
+    batches = [g.PolynomialBatch.from_values(list(splitmix_columns(s, w, n)), f["rate_bits"], False, f["cap_height"], ctx=ctx)
+               for s, w in zip(f["col_seeds"], f["widths"])]
+    ch = g.Challenger(ctx)
+    ch.observe_elements(f["transcript_prefix"])
+    instance = [g.FriBatchInfo(b["point"], [tuple(x) for x in b["polynomials"]]) for b in f["batches"]]
+    dbg = {}
+    params = g.FriParams(f["rate_bits"], f["cap_height"], f["arity_bits"])
+    head = g.prove_openings(instance, batches, ch, params, proof_of_work_bits=f["pow_bits"], ctx=ctx, debug=dbg)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u8").tobytes()).hexdigest()
+    assert sha(dbg["final_poly"]) == f["sha256_final_poly"]
+    assert [sha(q) for q in dbg["quotients"]] == f["sha256_quotients"]
+    assert [[int(x) for x in t.cap.flatten()] for t in head.trees] == f["commit_phase_caps"]
+    assert [[int(a), int(b)] for a, b in head.final_poly] == f["fri_final_poly"]
+    assert head.pow_witness == f["pow_witness"]
+    rounds = g.fri_prover_query_rounds([b.merkle_tree for b in batches], head.trees, ch, len(f["query_indices"]), params)
+    assert [r["x_index"] for r in rounds] == f["query_indices"]

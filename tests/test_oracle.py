@@ -336,3 +336,25 @@ def test_fri_query_rounds_restatement_verifies():
             assert [w for e in evals for w in e] == list(leaf)
             assert o.verify_merkle_proof_to_cap(leaf, x >> arity_bits, tree.cap, step["merkle_proof"])
             x >>= arity_bits
+
+
+def test_openings_fri_golden_fixture_python_oracle(golden):
+    """The Python big-int restatement reproduces the committed openings/FRI fixture (generated by the C oracle)."""
+    f = golden["openings_fri"]
+    n = 1 << f["log_n"]
+    cols = [splitmix_columns(s, w, n) for s, w in zip(f["col_seeds"], f["widths"])]
+    coeffs = [[o.ifft([int(v) for v in c]) for c in x] for x in cols]
+    ch = o.Challenger()
+    ch.observe_elements(f["transcript_prefix"])
+    alpha = ch.get_extension_challenge()
+    assert list(alpha) == f["alpha"]
+    batches = [(tuple(b["point"]), [tuple(x) for x in b["polynomials"]]) for b in f["batches"]]
+    final, quots = o.prove_openings_final_poly(batches, coeffs, alpha)
+    sha = lambda a: hashlib.sha256(np.array(a, dtype="<u8").tobytes()).hexdigest()
+    assert sha(final) == f["sha256_final_poly"] and [sha(q) for q in quots] == f["sha256_quotients"]
+    lde, vals = o.prove_openings_lde(final, f["rate_bits"])
+    trees, fp = o.fri_committed_trees(lde, vals, ch, f["arity_bits"], f["rate_bits"], f["cap_height"])
+    assert [[w for h in t.cap for w in h] for t in trees] == f["commit_phase_caps"]
+    assert [list(e) for e in fp] == f["fri_final_poly"]
+    assert o.fri_proof_of_work(ch, f["pow_bits"]) == f["pow_witness"]
+    assert [ch.get_challenge() % (n << f["rate_bits"]) for _ in f["query_indices"]] == f["query_indices"]
