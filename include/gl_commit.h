@@ -1,7 +1,8 @@
 /*
  * gl_commit.h — C ABI of libgl_commit: the B200-native (sm_100a) replacement for the commitment hot path of the
  * plonky2 prover that plonky2.5 drives (PolynomialBatch::from_values / from_coeffs, MerkleTree::new,
- * fri_committed_trees).  This is the drop-in boundary: plain C, `uint64_t` Goldilocks words (little-endian,
+ * fri_committed_trees; and, next to it, the front half of prove_openings, the proof-of-work grind and the query-round
+ * openings, so that the committed data never has to leave the device).  This is the drop-in boundary: plain C, `uint64_t` Goldilocks words (little-endian,
  * GoldilocksField is #[repr(transparent)] u64; inputs may be non-canonical, outputs are always canonical),
  * integer status returns, no unwinding across the boundary, no torch types.
  *
@@ -11,7 +12,7 @@
  *                                                  fri/oracle.rs · prove_openings -> fri/prover.rs · fri_committed_trees
  * (and the 23 other prove/verify pairs listed in SURVEY.md §4).  The upstream functions live in the un-vendored crate
  * plonky2 @ 3de92d9ed1721cec133e4e1e1b3ec7facb756ccf (Cargo.toml:15-19); each entry point below names the upstream
- * item it replaces.  The Rust binding a maintainer would add is shown in INTEGRATION.md / ffi/rust/.
+ * item it replaces.  The Rust binding a maintainer would add is shown in INTEGRATION.md.
  *
  * Threading: every call takes the context's mutex; calls on one context are serialised, distinct contexts are
  * independent (one context per prover thread is the intended use under `cargo test`'s parallel tests).

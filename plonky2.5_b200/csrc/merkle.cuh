@@ -66,7 +66,7 @@ leaf_hash_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t l
 
 // One thread per node of layer `layer` (1..log_sub): two_to_one(children).
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, LEAF_MIN_BLOCKS)
 tree_level_kernel(uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, uint32_t layer, uint32_t log_sub,
                   uint64_t n_nodes) {
     uint64_t node = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
