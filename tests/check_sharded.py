@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check (run under torchrun on N GPUs): the sharded commit's cap and every rank's digests slice
 must equal the single-GPU commit and the CPU oracle on the same seeded columns.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_sharded.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/check_sharded.py
 """
 import ctypes
 import os

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Build and time compile-time variants of libgl_commit.so (development aid; the product library is the default build).
 
-    python tools/variants.py build            # here (no GPU): nvcc each variant into plonky2.5_b200/variants/
-    python tools/variants.py run [names...]   # on the GPU box: KAT check + leaf-hash / LDE timing of each variant
+    python tests/variants.py build            # here (no GPU): nvcc each variant into plonky2.5_b200/variants/
+    python tests/variants.py run [names...]   # on the GPU box: KAT check + leaf-hash / LDE timing of each variant
 Each variant runs in its own process (one CUDA library per process)."""
 import json, os, subprocess, sys
 

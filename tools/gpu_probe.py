@@ -6,12 +6,11 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT]
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import plonky25_b200 as g  # noqa: E402
-from oracle_c import splitmix_columns  # noqa: E402
 
 
 def main():
