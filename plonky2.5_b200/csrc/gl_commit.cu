@@ -958,8 +958,9 @@ int gl_tree_get_lde_values(gl_ctx* c, gl_handle h, uint64_t index, uint64_t step
 int gl_tree_prove(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_siblings) {
     GL_API_BEGIN(c)
     Tree* t = find_tree(c, h);
-    if (leaf_index >= t->n_leaves || !out_siblings) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
+    if (leaf_index >= t->n_leaves) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
     uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
+    if (!out_siblings && log_sub) GL_THROW(GL_ERR_INVALID, "out_siblings is NULL");   /* an empty proof needs no buffer */
     uint64_t L = 1ULL << log_sub, sub = leaf_index >> log_sub, j = leaf_index & (L - 1);
     const uint64_t* base = t->digests.p + 4 * (sub * 2 * (L - 1));
     for (uint32_t layer = 0; layer < log_sub; layer++) {
