@@ -10,6 +10,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 
 #include "gl_plonky2.hpp"
 
@@ -457,6 +458,48 @@ static void test_prove_openings(Context& ctx, const Golden* golden) {
     CHECK(panics_with("out of range", [&] { PolynomialBatch::prove_openings(bad2, {&a}, ch, p, nullptr, &ctx); }), "polynomial index must panic");
 }
 
+// `cargo test` proves from several threads at once: every thread gets its own Context (Context::thread_default(), as the
+// Rust shim's thread_local CTX) and commits / opens concurrently; results must not depend on what the other threads do.
+static void test_concurrent_contexts() {
+    constexpr int T = 4;
+    int bad[T] = {0, 0, 0, 0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([t, &bad] {
+            try {
+                for (int it = 0; it < 3; it++) {
+                    const unsigned log_n = 7 + t, c = 20 + 5 * t + it, r = 1 + (t & 1) * 2, h = 2;
+                    const size_t n = size_t(1) << log_n, R = n << r;
+                    auto cols = splitmix_columns(4000 + 10 * t + it, c, n);
+                    std::vector<const uint64_t*> p;
+                    for (auto& v : cols) p.push_back(v.data());
+                    std::vector<F> leaves(R * c), digests(8 * (R - (size_t(1) << h))), cap(4 << h);
+                    if (glo_commit(p.data(), c, log_n, r, h, 0, nullptr, leaves.data(), digests.data(), cap.data(), nullptr)) bad[t]++;
+                    PolynomialBatch pb = PolynomialBatch::from_values(as_values(cols), r, false, h);   // Context::thread_default()
+                    if (pb.merkle_tree.cap.flatten() != cap) bad[t]++;
+                    const size_t x = (R / 3) ^ size_t(t);
+                    auto opened = pb.merkle_tree.open_batch({x, R - 1});
+                    if (opened[0].first != std::vector<F>(leaves.begin() + x * c, leaves.begin() + (x + 1) * c)) bad[t]++;
+                    if (!verify_path(opened[0].first, x, opened[0].second, pb.merkle_tree.cap)) bad[t]++;
+                    if (!verify_path(opened[1].first, R - 1, opened[1].second, pb.merkle_tree.cap)) bad[t]++;
+                    Challenger ch;                                                              // same thread-local context
+                    ch.observe_cap(pb.merkle_tree.cap);
+                    FriConfig cfg; cfg.proof_of_work_bits = 6;
+                    const F w = fri_proof_of_work(ch, cfg);
+                    glo_challenger ref;
+                    glo_challenger_init(&ref);
+                    glo_challenger_observe(&ref, cap.data(), cap.size());
+                    if (w != glo_fri_proof_of_work(&ref, 6)) bad[t]++;
+                }
+            } catch (const std::exception& e) {
+                std::printf("thread %d: %s\n", t, e.what());
+                bad[t] += 100;
+            }
+        });
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; t++) CHECK(bad[t] == 0, "thread %d: %d mismatches", t, bad[t]);
+}
+
 int main(int argc, char** argv) {
     bool expect_no_device = false;
     const char* golden_path = nullptr;
@@ -488,6 +531,8 @@ int main(int argc, char** argv) {
         std::printf("fri_proof: %d checks, %d failed\n", g_checks, g_fail);
         test_prove_openings(ctx, golden_path ? &golden : nullptr);
         std::printf("prove_openings: %d checks, %d failed\n", g_checks, g_fail);
+        test_concurrent_contexts();
+        std::printf("concurrent contexts: %d checks, %d failed\n", g_checks, g_fail);
     } catch (const std::exception& e) {
         std::printf("FAIL: unexpected exception: %s\n", e.what());
         return 2;

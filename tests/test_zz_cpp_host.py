@@ -28,7 +28,7 @@ def build_host_mirror_test() -> str:
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC, "-o", BIN,
            "-L", os.path.dirname(lib), "-lgl_commit", "-L", os.path.dirname(ora), "-lgl_oracle",
-           "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-Wl,-rpath,$ORIGIN/../../../oracle"]
+           "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-Wl,-rpath,$ORIGIN/../../../oracle", "-pthread"]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.run(cmd, check=True, env=env)
@@ -50,7 +50,7 @@ def build_host_mirror_test_double() -> str:
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC, dbl, "-o", exe,
-                    "-L", os.path.dirname(ora), "-lgl_oracle", "-Wl,-rpath,$ORIGIN/../../../oracle"], check=True, env=env)
+                    "-L", os.path.dirname(ora), "-lgl_oracle", "-Wl,-rpath,$ORIGIN/../../../oracle", "-pthread"], check=True, env=env)
     return exe
 
 
