@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <algorithm>
+#include <exception>
 #include <cstring>
 #include <cstdlib>
 #include <map>
@@ -99,6 +100,9 @@ struct DevBuf {
         words = w;
     }
     void release() {
+        // Released while an error unwinds the call: kernels or copies enqueued before the failure may still be touching the
+        // buffer, and the pool is shared with other contexts — wait for the device before handing it on (error path only).
+        if (p && std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
         if (p) DevPool::get().give(dev, words, p);
         p = nullptr;
         words = 0;
@@ -604,7 +608,8 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
     catch (const GlError& e) {                   \
         (ctx)->err = e.msg;                      \
         cudaGetLastError();                      \
-        if ((ctx)->copy_stream) cudaStreamSynchronize((ctx)->copy_stream); /* host buffers are only borrowed */ \
+        if ((ctx)->stream) cudaStreamSynchronize((ctx)->stream);           /* host buffers are only borrowed: nothing may */ \
+        if ((ctx)->copy_stream) cudaStreamSynchronize((ctx)->copy_stream); /* read or write them after the call returns  */ \
         if ((ctx)->send_stream) cudaStreamSynchronize((ctx)->send_stream);                                      \
         return e.code;                           \
     }                                            \
