@@ -191,7 +191,7 @@ struct gl_ctx {
     std::set<const uint64_t*> own_ipc;    // buffers exported by gl_dev_ipc_alloc (to tell the local leaf buffer from mapped peers)
     bool trace = false;                    // GL_TRACE=1: per-coset timeline of the overlapped exchange on stderr (development aid)
     std::vector<cudaEvent_t> trace_ev;     // base, then per coset: ntt start, ntt end, send start, send end
-    cudaEvent_t ev_sync = nullptr;
+    cudaEvent_t ev_sync = nullptr, ev_copyback = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t ev[GL_N_STAGES + 1] = {};
     float stage_ms[GL_N_STAGES] = {};
@@ -568,11 +568,9 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
         record(c, GL_STAGE_TRANSPOSE);
         lde_stage(c, d_cols_in, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
     }
-    record(c, GL_STAGE_LEAF_HASH);
-    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
-                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
-    record(c, GL_STAGE_D2H);
-    CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, (32ULL << cap_height), cudaMemcpyDeviceToHost, c->stream));
+    // Copy-back of the coefficients and the leaves (a host that materialises PolynomialBatch::polynomials / MerkleTree::leaves) leaves
+    // on the copy stream as soon as the LDE is done, i.e. PCIe runs while the tree is hashed; only the digests wait for the hash.
+    const bool early_copyback = out_coeffs || out_leaves;
     if (out_coeffs) {
         // row-major [N][pitch] -> column-major [n_cols][N] on the device, then one contiguous copy
         c->scratch.ensure(N * n_cols);
@@ -580,13 +578,24 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
         ntt::transpose_out_kernel<<<tg, tb, 0, c->stream>>>(t->coeffs.p, pitch, c->scratch.p, N, n_cols, N);
         CUDA_CHECK(cudaGetLastError());
         c->launches[GL_STAGE_D2H]++;
-        CUDA_CHECK(cudaMemcpyAsync(out_coeffs, c->scratch.p, N * n_cols * 8, cudaMemcpyDeviceToHost, c->stream));
     }
-    if (out_leaves)
-        CUDA_CHECK(cudaMemcpy2DAsync(out_leaves, (size_t)n_cols * 8, t->leaves.p, (size_t)pitch * 8, (size_t)n_cols * 8, R,
-                                     cudaMemcpyDeviceToHost, c->stream));
+    record(c, GL_STAGE_LEAF_HASH);
+    if (early_copyback) {
+        CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
+        if (out_coeffs) CUDA_CHECK(cudaMemcpyAsync(out_coeffs, c->scratch.p, N * n_cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (out_leaves)
+            CUDA_CHECK(cudaMemcpy2DAsync(out_leaves, (size_t)n_cols * 8, t->leaves.p, (size_t)pitch * 8, (size_t)n_cols * 8, R,
+                                         cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_CHECK(cudaEventRecord(c->ev_copyback, c->copy_stream));
+    }
+    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
+                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    record(c, GL_STAGE_D2H);
+    CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, (32ULL << cap_height), cudaMemcpyDeviceToHost, c->stream));
     if (out_digests && n_dig)
         CUDA_CHECK(cudaMemcpyAsync(out_digests, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (early_copyback) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copyback, 0));   // the d2h stage ends when everything has landed
     record(c, GL_N_STAGES);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < GL_N_STAGES; i++) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
@@ -661,6 +670,7 @@ int gl_ctx_create(gl_ctx** out, int device) {
     if (const char* m = getenv("GL_SCATTER_MODE")) c->scatter_mode = atoi(m);
     if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
     if (cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&c->ev_copyback, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     for (auto& e : c->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -683,6 +693,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    if (c->ev_copyback) cudaEventDestroy(c->ev_copyback);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->send_stream) { cudaStreamSynchronize(c->send_stream); cudaStreamDestroy(c->send_stream); }
     for (int i = 0; i < 2; i++) { if (c->ev_ntt[i]) cudaEventDestroy(c->ev_ntt[i]); if (c->ev_sent[i]) cudaEventDestroy(c->ev_sent[i]); }
