@@ -580,8 +580,13 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
         c->launches[GL_STAGE_D2H]++;
     }
     record(c, GL_STAGE_LEAF_HASH);
+    if (early_copyback) CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));
+    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
+                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    record(c, GL_STAGE_D2H);
     if (early_copyback) {
-        CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));
+        // enqueued after the hash kernels were launched: with pageable host memory these calls block the host thread while they
+        // run, and the GPU is already hashing by then — the overlap holds for a plain Vec / numpy array as well as for pinned memory
         CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
         if (out_coeffs) CUDA_CHECK(cudaMemcpyAsync(out_coeffs, c->scratch.p, N * n_cols * 8, cudaMemcpyDeviceToHost, c->copy_stream));
         if (out_leaves)
@@ -589,9 +594,6 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
                                          cudaMemcpyDeviceToHost, c->copy_stream));
         CUDA_CHECK(cudaEventRecord(c->ev_copyback, c->copy_stream));
     }
-    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
-                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
-    record(c, GL_STAGE_D2H);
     CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, (32ULL << cap_height), cudaMemcpyDeviceToHost, c->stream));
     if (out_digests && n_dig)
         CUDA_CHECK(cudaMemcpyAsync(out_digests, t->digests.p, n_dig * 32, cudaMemcpyDeviceToHost, c->stream));

@@ -6,7 +6,7 @@
 //              MerkleTree::leaves / digests, SURVEY.md §8d "what the Rust drop-in would pay")
 // Wall-clock around the synchronous calls (std::chrono), W warm-up + K timed calls, one JSON line per (shape, mode).
 // Build: g++ -std=c++17 -O2 -I include tools/cbench.cpp -o build/cbench -L plonky2.5_b200 -lgl_commit -pthread
-// Usage: cbench [log_n n_cols rate_bits cap_height copyback(0/1)]...      (default: cfg2 cap, cfg2 copyback, cfg3 cap)
+// Usage: cbench [log_n n_cols rate_bits cap_height mode(0 cap / 1 copyback pinned / 2 copyback pageable)]...   (default: cfg2 x3 modes, cfg3 cap)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +27,8 @@ static void fill(uint64_t* col, uint64_t n, uint64_t first_index) {   // tests/o
     }
 }
 
-static int run(gl_ctx* ctx, unsigned log_n, unsigned n_cols, unsigned r, unsigned h, bool copyback, int warmup, int steps) {
+static int run(gl_ctx* ctx, unsigned log_n, unsigned n_cols, unsigned r, unsigned h, int mode, int warmup, int steps) {
+    const bool copyback = mode != 0, pageable = mode == 2;   // 2: outputs in plain malloc memory (a Rust Vec / numpy array)
     const uint64_t N = 1ULL << log_n, R = N << r, n_dig = 2 * (R - (1ULL << h));
     uint64_t* in = (uint64_t*)gl_host_alloc(N * n_cols * 8);
     if (!in) { std::printf("{\"error\": \"pinned allocation failed\"}\n"); return 1; }
@@ -42,9 +43,9 @@ static int run(gl_ctx* ctx, unsigned log_n, unsigned n_cols, unsigned r, unsigne
     for (unsigned j = 0; j < n_cols; j++) cols[j] = in + (uint64_t)j * N;
     uint64_t *oc = nullptr, *ol = nullptr, *od = nullptr;
     if (copyback) {
-        oc = (uint64_t*)gl_host_alloc(N * n_cols * 8);
-        ol = (uint64_t*)gl_host_alloc(R * n_cols * 8);
-        od = (uint64_t*)gl_host_alloc(n_dig * 32);
+        oc = (uint64_t*)(pageable ? std::malloc(N * n_cols * 8) : gl_host_alloc(N * n_cols * 8));
+        ol = (uint64_t*)(pageable ? std::malloc(R * n_cols * 8) : gl_host_alloc(R * n_cols * 8));
+        od = (uint64_t*)(pageable ? std::malloc(n_dig * 32) : gl_host_alloc(n_dig * 32));
         if (!oc || !ol || !od) { std::printf("{\"error\": \"pinned allocation failed\"}\n"); return 1; }
     }
     std::vector<uint64_t> cap(4ULL << h), cap0;
@@ -88,13 +89,14 @@ static int run(gl_ctx* ctx, unsigned log_n, unsigned n_cols, unsigned r, unsigne
                 "\"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"gpu_launches_per_call\": %u, "
                 "\"stage_ms_last\": {\"h2d\": %.3f, \"transpose\": %.3f, \"intt\": %.3f, \"lde\": %.3f, \"leaf_hash\": %.3f, \"tree\": %.3f, \"d2h\": %.3f}, "
                 "\"cap0\": \"%016llx\", \"verified\": \"%s\"}\n",
-                copyback ? "copyback (coeffs + leaves + digests + cap to pinned host)" : "cap (outputs stay in HBM)", log_n, n_cols, r, h,
+                pageable ? "copyback (coeffs + leaves + digests + cap to PAGEABLE host memory)" : copyback ? "copyback (coeffs + leaves + digests + cap to pinned host)" : "cap (outputs stay in HBM)", log_n, n_cols, r, h,
                 (double)N * n_cols / (ms * 1e3), ms, best_ms, steps, warmup, (unsigned long long)(N * n_cols * 8),
                 (unsigned long long)((copyback ? N * n_cols * 8 + R * n_cols * 8 + n_dig * 32 : 0) + (32ULL << h)), launches, st[0], st[1], st[2], st[3], st[4],
                 st[5], st[6], (unsigned long long)cap[0], verified);
     std::fflush(stdout);
     gl_host_free(in);
-    if (copyback) { gl_host_free(oc); gl_host_free(ol); gl_host_free(od); }
+    if (copyback && pageable) { std::free(oc); std::free(ol); std::free(od); }
+    else if (copyback) { gl_host_free(oc); gl_host_free(ol); gl_host_free(od); }
     return 0;
 }
 
@@ -105,11 +107,12 @@ int main(int argc, char** argv) {
     int bad = 0;
     if (argc >= 6) {
         for (int i = 1; i + 4 < argc; i += 5)
-            bad |= run(ctx, atoi(argv[i]), atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]) != 0, 3, 5);
+            bad |= run(ctx, atoi(argv[i]), atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]), 3, 5);
     } else {
-        bad |= run(ctx, 16, 135, 3, 4, false, 3, 10);
-        bad |= run(ctx, 16, 135, 3, 4, true, 3, 10);
-        bad |= run(ctx, 20, 135, 3, 4, false, 3, 5);
+        bad |= run(ctx, 16, 135, 3, 4, 0, 3, 10);
+        bad |= run(ctx, 16, 135, 3, 4, 1, 3, 10);
+        bad |= run(ctx, 16, 135, 3, 4, 2, 3, 10);
+        bad |= run(ctx, 20, 135, 3, 4, 0, 3, 5);
     }
     gl_ctx_destroy(ctx);
     return bad;
