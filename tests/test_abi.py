@@ -78,3 +78,27 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "gl_oracle" not in text and "libgl_oracle" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_rust_ffi_matches_the_header():
+    """rust/gl-commit/src/ffi.rs is exactly what tools/gen_rust_ffi.py produces from include/gl_commit.h (one declaration per
+    prototype), and the safe wrappers in src/lib.rs only call symbols that exist (no Rust toolchain here: a textual check)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    ffi = open(os.path.join(ROOT, "rust", "gl-commit", "src", "ffi.rs")).read()
+    assert ffi == gen.generate(), "run `python tools/gen_rust_ffi.py` after changing include/gl_commit.h"
+    declared = set(re.findall(r"pub fn (gl_[a-z0-9_]+)\(", ffi))
+    assert sorted(declared) == _header_symbols()
+    # argument counts agree with the ctypes table (an independent transcription of the same header)
+    from plonky25_b200 import _lib
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        m = re.search(r"pub fn %s\((.*?)\)" % name, ffi, flags=re.S)
+        n_args = len([a for a in m.group(1).split(",") if a.strip()])
+        assert n_args == len(argtypes), name
+    lib_rs = open(os.path.join(ROOT, "rust", "gl-commit", "src", "lib.rs")).read()
+    used = set(re.findall(r"ffi::(gl_[a-z0-9_]+)\(", lib_rs))
+    assert used and used <= declared, used - declared
+    consts = set(re.findall(r"ffi::(GL_[A-Z_0-9]+)", lib_rs))
+    assert consts <= set(re.findall(r"pub const (GL_[A-Z_0-9]+)", ffi)), consts
