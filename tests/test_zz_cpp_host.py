@@ -103,6 +103,57 @@ def test_cpp_host_mirror_host_logic_on_abi_double(tmp_path):
     assert "glo_" not in nm, "libgl_commit.so must not reference the oracle"
 
 
+def _cxx(args):
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), *args], check=True, env=env)
+
+
+def build_cpp_tools() -> dict:
+    """tools/cbench.cpp (e2e through the C ABI from C++) and tests/cpp/variant_bench.cpp (parity + timing of library variants)"""
+    import plonky25_b200 as g
+    from oracle_c import build_oracle
+    lib, ora = g.build(), build_oracle()
+    os.makedirs(OUT_DIR, exist_ok=True)
+    out = {"cbench": os.path.join(OUT_DIR, "cbench"), "variant_bench": os.path.join(OUT_DIR, "variant_bench")}
+    hdr = os.path.join(ROOT, "include", "gl_commit.h")
+
+    def stale(exe, deps):
+        return not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps)
+
+    src = os.path.join(ROOT, "tools", "cbench.cpp")
+    if stale(out["cbench"], [src, hdr, lib]):
+        _cxx([src, "-o", out["cbench"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
+    src = os.path.join(ROOT, "tests", "cpp", "variant_bench.cpp")
+    if stale(out["variant_bench"], [src, hdr, ora]):
+        _cxx([src, "-o", out["variant_bench"], "-L", os.path.dirname(ora), "-lgl_oracle", "-Wl,-rpath,$ORIGIN/../../../oracle", "-ldl", "-pthread"])
+    return out
+
+
+def test_cpp_tools_build_and_refuse_to_run_without_a_device():
+    exe = build_cpp_tools()
+    if os.path.exists("/dev/nvidia0"):
+        pytest.skip("GPU present")
+    r = subprocess.run([exe["cbench"]], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2 and "no CPU fallback" in r.stdout
+    r = subprocess.run([exe["variant_bench"], "--log-n", "8", os.path.join(ROOT, "plonky2.5_b200", "libgl_commit.so")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_tools_on_gpu():
+    """cbench: copy-back (pinned) equals the resident batch; variant_bench: the product library is parity-green through dlopen"""
+    exe = build_cpp_tools()
+    r = subprocess.run([exe["cbench"], "12", "20", "1", "2", "1", "14", "135", "3", "4", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("copy-back == gl_tree_read of the resident batch") == 2, r.stdout[-3000:]
+    r = subprocess.run([exe["variant_bench"], "--log-n", "14", os.path.join(ROOT, "plonky2.5_b200", "libgl_commit.so")],
+                       capture_output=True, text=True, timeout=300)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0 and line["parity_2p10x135"] and line["parity_noncanonical"] and line["parity_2p12x9"], r.stdout[-3000:]
+
+
 @pytest.mark.gpu
 def test_cpp_host_mirror_matches_oracle_on_gpu(tmp_path):
     exe = build_host_mirror_test()

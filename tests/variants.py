@@ -3,7 +3,11 @@
 
     python tests/variants.py build            # here (no GPU): nvcc each variant into plonky2.5_b200/variants/
     python tests/variants.py run [names...]   # on the GPU box: KAT check + leaf-hash / LDE timing of each variant
-Each variant runs in its own process (one CUDA library per process)."""
+Each variant runs in its own process (one CUDA library per process).
+
+tests/cpp/variant_bench.cpp is the torch-free twin for short GPU calls (a C++ binary starts in milliseconds where `import torch`
+on a fresh box takes a minute):  tests/cpp/build/variant_bench plonky2.5_b200/libgl_commit.so plonky2.5_b200/variants/*.so
+checks every library against the C oracle and prints stage times for the 2^20 x 135 commit (one JSON line per library)."""
 import json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
