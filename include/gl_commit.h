@@ -68,6 +68,21 @@ int gl_commit(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_
               uint32_t cap_height, int input_is_coeffs, uint64_t* out_coeffs, uint64_t* out_leaves,
               uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_batch);
 
+/* ---- the same commit on several GPUs from ONE process (CircuitData::prove is one process; BASELINE north star: columns sharded
+ * across the GPUs of a box for the LDE, redistributed column->row over NVLink, hashed into per-GPU subtrees whose roots form the cap).
+ * ctxs: n_ctx distinct contexts (a power of two <= 16, normally one per device; 2^cap_height >= n_ctx, n_cols >= n_ctx).  Context g
+ * runs the iNTT + LDE of its column slice, receives leaf rows [g*R/n_ctx, (g+1)*R/n_ctx) from all contexts and hashes them.
+ * out_cap: 2^cap_height * 4 words.  out_trees[g]: handle ON ctxs[g] of a device-resident tree over that leaf range with
+ * cap_height - log2(n_ctx): leaf row i of the batch is gl_tree_get(ctxs[i / (R/n_ctx)], out_trees[i / (R/n_ctx)], i % (R/n_ctx)),
+ * and gl_tree_prove on it returns exactly MerkleTree::prove(i) (the subtree roots are cap entries, so no path crosses contexts).
+ * The shard trees carry no coefficient matrix (gl_tree_read(GL_PART_COEFFS) is refused) and gl_tree_get_lde_values does not
+ * apply to them.  All contexts are locked for the duration of the call; status and message are reported through ctxs[0].
+ * ROUND-1 STATUS: bit-exact on a B200 with 2, 4 and 8 contexts sharing ONE device (cap, every shard's leaves and digests, paths ==
+ * oracle; tests/test_gpu_parity.py); with one device per context the only additional step is cudaDeviceEnablePeerAccess, not yet run
+ * on hardware (GL_TEST_COMMIT_MULTI_DEVICES=N spreads the test's contexts over N GPUs).                                          */
+int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                    uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_trees);
+
 /* ---- MerkleTree::new  (plonky2 hash/merkle_tree.rs) ---------------------------------------------------------
  * leaves: n_leaves rows of leaf_len words, packed row-major on the host.  n_leaves must be a power of two. */
 int gl_merkle_new(gl_ctx* ctx, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t cap_height,

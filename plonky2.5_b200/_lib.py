@@ -33,6 +33,8 @@ SIGNATURES = {
     "gl_ctx_stream": (c_uint64, [c_void_p]),
     "gl_commit": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_uint32, c_int,
                           c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "gl_commit_multi": (c_int, [POINTER(c_void_p), c_uint32, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_uint32, c_int, c_void_p,
+                                POINTER(c_uint64)]),
     "gl_merkle_new": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, POINTER(c_uint64)]),
     "gl_tree_info": (c_int, [c_void_p, c_uint64, POINTER(TreeInfo)]),
     "gl_tree_get": (c_int, [c_void_p, c_uint64, c_uint64, c_void_p]),

@@ -278,6 +278,23 @@ class PolynomialBatch:
         return out
 
 
+def commit_multi(ctxs: Sequence[Context], values, rate_bits: int, cap_height: int, is_coeffs: bool = False) -> Tuple[MerkleCap, List[MerkleTree]]:
+    """PolynomialBatch::from_values / from_coeffs on several GPUs from one process (gl_commit_multi): one Context per device, columns
+    sharded for the LDE, leaf ranges hashed per context.  Returns (cap, shard trees); leaf row i of the batch lives in
+    trees[i // (R // len(ctxs))] at local index i % (R // len(ctxs)), and `.prove` there is MerkleTree::prove(i)."""
+    cols, log_n = PolynomialBatch._cols(values)
+    if cap_height > 40:
+        raise ValueError("cap_height should be at most log2(leaves.len())")
+    lib = ctxs[0].lib
+    hs = (c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+    ptrs = (c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    cap = np.zeros(4 << cap_height, dtype=np.uint64)
+    trees = (c_uint64 * len(ctxs))()
+    _check(ctxs[0], lib.gl_commit_multi(hs, len(ctxs), ptrs, len(cols), log_n, rate_bits, cap_height, int(is_coeffs), _ptr(cap), trees))
+    per = (4 << cap_height) // len(ctxs)
+    return MerkleCap(cap), [MerkleTree(c, int(t), cap[g * per:(g + 1) * per].copy()) for g, (c, t) in enumerate(zip(ctxs, trees))]
+
+
 class Challenger:
     """plonky2 iop/challenger.rs · Challenger<F, PoseidonHash>: duplex sponge; the permutation runs on the GPU."""
 

@@ -10,7 +10,9 @@
 #include <exception>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
 #include <map>
+#include <thread>
 #include <utility>
 #include <memory>
 #include <mutex>
@@ -749,7 +751,8 @@ int gl_dev_lde(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
 
 static int lde_scatter_impl(gl_ctx* c, const uint64_t* d_cols, const uint64_t* const* host_cols, uint64_t col_stride, uint32_t n_cols,
                             uint32_t log_n, uint32_t rate_bits, int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers,
-                            uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset) {
+                            uint32_t leaf_pitch, uint32_t col_off, uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset,
+                            int self_hint = -1) {
     check_shape(n_cols, log_n, rate_bits, 0);
     if ((!d_cols && !host_cols) || !peer_leaves || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
     if (n_peers == 0 || (n_peers & (n_peers - 1)) || n_peers > ntt::MAX_PEERS) GL_THROW(GL_ERR_INVALID, "n_peers must be a power of two <= %d", ntt::MAX_PEERS);
@@ -771,6 +774,7 @@ static int lde_scatter_impl(gl_ctx* c, const uint64_t* d_cols, const uint64_t* c
     sc.self = ntt::MAX_PEERS;                 // which peer buffer is this rank's own (allocated by gl_dev_ipc_alloc on this context)?
     for (uint32_t q = 0; q < n_peers; q++)
         if (c->own_ipc.count(peer_leaves[q])) { sc.self = q; break; }
+    if (self_hint >= 0 && (uint32_t)self_hint < n_peers) sc.self = (uint32_t)self_hint;   // gl_commit_multi knows its rank
     get_roots(c, log_n);
     get_lde_tables(c, log_n, rate_bits);
     c->scratch.ensure(N * coeff_pitch);      // pass scratch of one coset
@@ -939,6 +943,200 @@ int gl_merkle_new(gl_ctx* c, const uint64_t* leaves, uint64_t n_leaves, uint32_t
     if (out_tree) *out_tree = put_tree(c, std::move(t));
     return GL_OK;
     GL_API_END(c)
+}
+
+// ---- one process, several GPUs -------------------------------------------------------------------------------------------------
+// CircuitData::prove runs in ONE process; a prover that owns several GPUs of the box calls gl_commit_multi with one context per
+// device.  Same plan as the one-process-per-GPU path (plonky2.5_b200/sharded.py): rank g = ctxs[g] runs the iNTT + LDE
+// of its column slice (columns dealt in groups of 4 so that every slice starts sector aligned), every coset's rows reach the rank
+// that owns that leaf range (peer copies behind the next coset's NTT; own rows stored by the NTT itself), the ranks meet once, and
+// every rank hashes its contiguous leaf range = whole cap subtrees.  One worker thread per context; in a single process peer
+// buffers are plain device pointers (unified addressing), so there is no IPC.
+namespace {
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    uint32_t n, waiting = 0, phase = 0;
+    explicit HostBarrier(uint32_t n_) : n(n_) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const uint32_t ph = phase;
+        if (++waiting == n) { waiting = 0; phase++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return phase != ph; });
+    }
+};
+
+struct MultiPlan {   // ShardPlan of plonky2.5_b200/sharded.py
+    std::vector<uint32_t> col_counts, col_offsets, pitches;
+    MultiPlan(uint32_t n_cols, uint32_t world) : col_counts(world), col_offsets(world), pitches(world) {
+        const uint32_t n_groups = (n_cols + 3) / 4;
+        if (n_groups >= world) {
+            const uint32_t base = n_groups / world, rem = n_groups % world;
+            for (uint32_t g = 0; g < world; g++) col_counts[g] = 4 * (base + (g < rem ? 1 : 0));
+            col_counts[world - 1] -= 4 * n_groups - n_cols;   // the last group may be partial
+        } else {
+            const uint32_t base = n_cols / world, rem = n_cols % world;
+            for (uint32_t g = 0; g < world; g++) col_counts[g] = base + (g < rem ? 1 : 0);
+        }
+        uint32_t off = 0;
+        for (uint32_t g = 0; g < world; g++) {
+            col_offsets[g] = off;
+            off += col_counts[g];
+            const uint32_t c = col_counts[g];
+            pitches[g] = (round_up(c, 8) - c < 4) ? round_up(c, 8) : round_up(c, 4);
+        }
+    }
+};
+}  // namespace
+
+int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                    uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_trees) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return GL_ERR_INVALID;
+    gl_ctx* c0 = ctxs[0];
+    auto fail0 = [&](int code, const char* msg) { std::lock_guard<std::mutex> lk(c0->mu); c0->err = msg; return code; };
+    if ((n_ctx & (n_ctx - 1)) || n_ctx > (uint32_t)ntt::MAX_PEERS) return fail0(GL_ERR_INVALID, "n_ctx must be a power of two <= 16");
+    for (uint32_t g = 0; g < n_ctx; g++) {
+        if (!ctxs[g]) return fail0(GL_ERR_INVALID, "NULL context");
+        for (uint32_t q = 0; q < g; q++)
+            if (ctxs[q] == ctxs[g]) return fail0(GL_ERR_INVALID, "the same context appears twice");
+    }
+    if (!cols || !out_cap || !out_trees) return fail0(GL_ERR_INVALID, "NULL pointer");
+    if (n_cols < n_ctx) return fail0(GL_ERR_INVALID, "fewer columns than contexts");
+    if (log_n + rate_bits > 31) return fail0(GL_ERR_UNSUPPORTED, "log_n + rate_bits > 31");
+    if (cap_height > log_n + rate_bits) return fail0(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len())");
+    if ((1ULL << cap_height) < n_ctx) return fail0(GL_ERR_INVALID, "cap_height too small: every context must own at least one whole cap subtree");
+    for (uint32_t j = 0; j < n_cols; j++)
+        if (!cols[j]) return fail0(GL_ERR_INVALID, "cols[j] is NULL");
+
+    const uint32_t G = n_ctx, log_g = log2_exact(G), local_cap_height = cap_height - log_g;
+    const uint64_t N = 1ULL << log_n, R = N << rate_bits, rows_per_rank = R / G;
+    const uint32_t leaf_pitch = round_up(n_cols, 8);
+    const MultiPlan plan(n_cols, G);
+    std::vector<uint64_t*> peer_leaves(G, nullptr);
+    std::vector<std::unique_ptr<Tree>> trees(G);
+    std::vector<int> rcs(G, GL_OK);
+    HostBarrier barrier(G);
+
+    auto worker = [&](uint32_t g) {
+        gl_ctx* c = ctxs[g];
+        std::lock_guard<std::mutex> lk(c->mu);
+        // every phase is tried separately: a rank that failed still arrives at the barriers, so nobody waits forever
+        auto phase = [&](auto&& body) {
+            if (rcs[g] != GL_OK) return;
+            try {
+                body();
+            } catch (const GlError& e) {
+                c->err = e.msg;
+                cudaGetLastError();
+                if (c->stream) cudaStreamSynchronize(c->stream);
+                if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+                if (c->send_stream) cudaStreamSynchronize(c->send_stream);
+                rcs[g] = e.code;
+            } catch (const std::bad_alloc&) {
+                c->err = "host allocation failed";
+                rcs[g] = GL_ERR_OOM;
+            }
+        };
+        phase([&] {   // A: this rank's leaf range, digests and sub-cap; peers become addressable
+            CUDA_CHECK(cudaSetDevice(c->device));
+            auto t = std::make_unique<Tree>();
+            t->n_leaves = rows_per_rank; t->leaf_len = n_cols; t->pitch = leaf_pitch; t->cap_height = local_cap_height;
+            t->leaves.ensure(rows_per_rank * leaf_pitch);
+            t->digests.ensure(2 * (rows_per_rank - (1ULL << local_cap_height)) * 4);
+            t->d_cap.ensure(4ULL << local_cap_height);
+            t->cap.resize(4ULL << local_cap_height);
+            t->coeffs.ensure(N * plan.pitches[g]);   // this rank's coefficient slice [N][pitch_g] (not served by gl_tree_read: has_coeffs stays false)
+            for (uint32_t q = 0; q < G; q++) {
+                if (ctxs[q]->device == c->device) continue;
+                int can = 0;
+                CUDA_CHECK(cudaDeviceCanAccessPeer(&can, c->device, ctxs[q]->device));
+                if (!can) GL_THROW(GL_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, ctxs[q]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else CUDA_CHECK(e);
+            }
+            peer_leaves[g] = t->leaves.p;
+            trees[g] = std::move(t);
+        });
+        barrier.arrive_and_wait();               // all leaf buffers exist
+        bool all_ok = true;
+        for (uint32_t q = 0; q < G; q++) all_ok = all_ok && rcs[q] == GL_OK;
+        if (all_ok)
+            phase([&] {   // B: iNTT + LDE of the column slice; every coset's rows go to their owners
+                CUDA_CHECK(cudaSetDevice(c->device));
+                const uint32_t n_cosets = 1u << rate_bits;
+                const uint32_t first_coset = rate_bits ? h_bitrev((uint32_t)(((uint64_t)g * n_cosets / G) % n_cosets), rate_bits) : 0;
+                lde_scatter_impl(c, nullptr, cols + plan.col_offsets[g], 0, plan.col_counts[g], log_n, rate_bits, input_is_coeffs, peer_leaves.data(), G,
+                                 leaf_pitch, plan.col_offsets[g], trees[g]->coeffs.p, plan.pitches[g], first_coset, (int)g);
+            });
+        barrier.arrive_and_wait();               // every rank's shipments have landed (lde_scatter_impl returns after its last copy)
+        all_ok = true;
+        for (uint32_t q = 0; q < G; q++) all_ok = all_ok && rcs[q] == GL_OK;
+        if (all_ok)
+            phase([&] {   // C: hash the own leaf range down to this rank's slice of the cap
+                CUDA_CHECK(cudaSetDevice(c->device));
+                Tree* t = trees[g].get();
+                for (int i : {GL_STAGE_LEAF_HASH, GL_STAGE_TREE, GL_STAGE_D2H}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+                record(c, GL_STAGE_LEAF_HASH);
+                merkle_build(c, t->leaves.p, rows_per_rank, n_cols, leaf_pitch, local_cap_height, t->digests.p, t->d_cap.p,
+                             &c->launches[GL_STAGE_LEAF_HASH], &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+                record(c, GL_STAGE_D2H);
+                CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, 32ULL << local_cap_height, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                for (int i : {GL_STAGE_LEAF_HASH, GL_STAGE_TREE}) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+            });
+        barrier.arrive_and_wait();               // nobody releases a leaf buffer a peer may still be copying into
+    };
+
+    // workers wait at a gate until every thread exists: if one cannot be started, the others leave without touching a barrier
+    std::mutex gate_mu;
+    std::condition_variable gate_cv;
+    int gate = 0;   // 0 wait, 1 go, -1 cancel
+    auto gated_worker = [&](uint32_t g) {
+        {
+            std::unique_lock<std::mutex> lk(gate_mu);
+            gate_cv.wait(lk, [&] { return gate != 0; });
+            if (gate < 0) return;
+        }
+        worker(g);
+    };
+    std::vector<std::thread> threads;
+    bool started = true;
+    try {
+        for (uint32_t g = 1; g < G; g++) threads.emplace_back(gated_worker, g);
+    } catch (...) {
+        started = false;
+    }
+    {
+        std::lock_guard<std::mutex> lk(gate_mu);
+        gate = started ? 1 : -1;
+    }
+    gate_cv.notify_all();
+    if (started) worker(0);
+    for (auto& t : threads) t.join();
+    if (!started) return fail0(GL_ERR_OOM, "could not start the worker threads");
+
+    int rc = GL_OK;
+    for (uint32_t g = 0; g < G && rc == GL_OK; g++) rc = rcs[g];
+    if (rc != GL_OK) {
+        for (uint32_t g = 0; g < G; g++) {
+            std::lock_guard<std::mutex> lk(ctxs[g]->mu);
+            cudaSetDevice(ctxs[g]->device);
+            trees[g].reset();
+        }
+        if (rcs[0] == GL_OK) {   // report through the first context what a peer said
+            for (uint32_t g = 1; g < G; g++)
+                if (rcs[g] != GL_OK) { std::string m; { std::lock_guard<std::mutex> lk(ctxs[g]->mu); m = ctxs[g]->err; } fail0(rcs[g], m.c_str()); break; }
+        }
+        return rc;
+    }
+    // rank q owns cap entries [q * 2^h / G, (q + 1) * 2^h / G)
+    for (uint32_t g = 0; g < G; g++) {
+        memcpy(out_cap + (size_t)g * (4ULL << local_cap_height), trees[g]->cap.data(), 32ULL << local_cap_height);
+        std::lock_guard<std::mutex> lk(ctxs[g]->mu);
+        out_trees[g] = put_tree(ctxs[g], std::move(trees[g]));
+    }
+    return GL_OK;
 }
 
 int gl_tree_info(gl_ctx* c, gl_handle h, gl_tree_info_t* out) {

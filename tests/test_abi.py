@@ -102,3 +102,9 @@ def test_rust_ffi_matches_the_header():
     assert used and used <= declared, used - declared
     consts = set(re.findall(r"ffi::(GL_[A-Z_0-9]+)", lib_rs))
     assert consts <= set(re.findall(r"pub const (GL_[A-Z_0-9]+)", ffi)), consts
+
+
+def test_commit_multi_rejects_null_without_touching_a_device():
+    from plonky25_b200 import _lib
+    lib = _lib.load()
+    assert lib.gl_commit_multi(None, 2, None, 4, 3, 1, 1, 0, None, None) == _lib.GL_ERR_INVALID

@@ -2,6 +2,8 @@
 import hashlib
 import random
 
+import os
+
 import numpy as np
 import pytest
 
@@ -402,3 +404,37 @@ def test_openings_fri_golden_fixture_on_gpu(ctx, golden):
     assert head.pow_witness == f["pow_witness"]
     rounds = g.fri_prover_query_rounds([b.merkle_tree for b in batches], head.trees, ch, len(f["query_indices"]), params)
     assert [r["x_index"] for r in rounds] == f["query_indices"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(2, 8, 20, 1, 1), (2, 10, 135, 3, 4), (4, 9, 33, 2, 2), (4, 10, 135, 3, 4), (8, 7, 9, 3, 3), (2, 3, 2, 0, 1)])
+def test_commit_multi_single_process(oc, cfg):
+    """gl_commit_multi with n contexts (here all on device 0: the plan, the shipments and the per-range hashing are the same as
+    with one device per context): cap, every shard's leaves and digests, rows and paths equal the single commit of the oracle."""
+    g = _g()
+    world, log_n, n_cols, r, cap_h = cfg
+    n_dev = int(os.environ.get("GL_TEST_COMMIT_MULTI_DEVICES", "1"))     # > 1: spread the contexts over that many GPUs
+    ctxs = [g.Context(k % n_dev) for k in range(world)]
+    try:
+        cols = splitmix_columns(700 + world + log_n, n_cols, 1 << log_n)
+        ref = oc.commit(cols, r, cap_h)
+        for rep in range(2):                       # buffers and peer mappings are reused by the second call
+            cap, trees = g.commit_multi(ctxs, list(cols), r, cap_h)
+            assert np.array_equal(cap.hashes, ref["cap"])
+            rows = (1 << (log_n + r)) // world
+            dig_per = 2 * (rows - (1 << (cap_h - (world.bit_length() - 1))))
+            for q, t in enumerate(trees):
+                assert (t.n_leaves, t.leaf_len, t.cap_height) == (rows, n_cols, cap_h - (world.bit_length() - 1))
+                assert np.array_equal(t.leaves, ref["leaves"][q * rows:(q + 1) * rows])
+                assert np.array_equal(t.digests, ref["digests"][q * dig_per:(q + 1) * dig_per])
+                for i in {0, rows - 1, rows // 3}:
+                    assert oc.verify_path(t.get(i), q * rows + i, t.prove(i), ref["cap"])
+            for t in trees:
+                t.free()
+        with pytest.raises(ValueError, match="cap_height too small"):
+            g.commit_multi(ctxs, list(cols), r, 0)
+        with pytest.raises(ValueError, match="twice"):
+            g.commit_multi([ctxs[0], ctxs[0]], list(cols), r, cap_h)
+    finally:
+        for c in ctxs:
+            c.close()
