@@ -533,6 +533,50 @@ public:
         return proof;
     }
 
+    /* from_values on several GPUs from this one process (gl_commit_multi): one Context per device.  The batch comes back as one
+     * shard tree per context — leaf row i lives in shards[i / rows_per_shard] at local index i % rows_per_shard, and `prove` there is
+     * MerkleTree::prove(i) — under the cap of the whole batch. */
+    struct Sharded {
+        MerkleCap cap;
+        std::vector<MerkleTree> shards;
+        size_t degree_log = 0, rate_bits = 0;
+        size_t rows_per_shard() const { return shards.empty() ? 0 : shards[0].n_leaves(); }
+        std::vector<F> get(size_t i) const { return shards[i / rows_per_shard()].get(i % rows_per_shard()); }
+        MerkleProof prove(size_t i) const { return shards[i / rows_per_shard()].prove(i % rows_per_shard()); }
+    };
+    static Sharded from_values_multi(const std::vector<Context*>& ctxs, const std::vector<PolynomialValues>& values, size_t rate_bits, bool blinding,
+                                     size_t cap_height) {
+        if (blinding) throw Panic("blinding (zero_knowledge) is not on the GPU path: the reference runs with zk off (src/p3/mod.rs:231)");
+        if (ctxs.empty() || !ctxs[0]) throw Panic("from_values_multi: no contexts");
+        if (values.empty()) throw Panic("PolynomialBatch: empty polynomial batch");
+        const size_t n = values[0].len();
+        if (n == 0 || (n & (n - 1))) throw Panic("PolynomialBatch: polynomial length must be a power of two");
+        if (cap_height > 40) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
+        std::vector<const uint64_t*> cols;
+        for (const auto& v : values) {
+            if (v.len() != n) throw Panic("Polynomial degrees inconsistent");
+            cols.push_back(v.values.data());
+        }
+        std::vector<gl_ctx*> raw;
+        for (Context* c : ctxs) raw.push_back(c ? c->raw() : nullptr);
+        size_t log_n = 0;
+        while ((size_t(1) << log_n) < n) log_n++;
+        Sharded out;
+        out.cap.hashes.resize(size_t(1) << cap_height);
+        out.degree_log = log_n;
+        out.rate_bits = rate_bits;
+        std::vector<gl_handle> hs(ctxs.size(), 0);
+        ctxs[0]->check(gl_commit_multi(raw.data(), uint32_t(raw.size()), cols.data(), uint32_t(cols.size()), uint32_t(log_n), uint32_t(rate_bits),
+                                       uint32_t(cap_height), 0, out.cap.hashes[0].elements.data(), hs.data()));
+        const size_t per = out.cap.hashes.size() / ctxs.size();
+        for (size_t g = 0; g < ctxs.size(); g++) {
+            MerkleCap sub;
+            sub.hashes.assign(out.cap.hashes.begin() + g * per, out.cap.hashes.begin() + (g + 1) * per);
+            out.shards.emplace_back(*ctxs[g], hs[g], std::move(sub));
+        }
+        return out;
+    }
+
 private:
     static PolynomialBatch commit(const std::vector<const uint64_t*>& cols, size_t n, size_t rate_bits, bool blinding, size_t cap_height,
                                   int input_is_coeffs, Context* ctx) {

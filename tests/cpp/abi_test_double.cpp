@@ -110,6 +110,35 @@ int gl_commit(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t 
     return GL_OK;
 }
 
+// the sharded commit restated on the oracle: one commit, then every context gets its leaf range and its slice of the digests
+int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
+                    uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_trees) {
+    if (!ctxs || !n_ctx || !ctxs[0]) return GL_ERR_INVALID;
+    gl_ctx* c = ctxs[0];
+    if (n_ctx & (n_ctx - 1)) return c->fail(GL_ERR_INVALID, "n_ctx must be a power of two <= 16");
+    for (uint32_t g = 0; g < n_ctx; g++)
+        for (uint32_t q = 0; q < g; q++)
+            if (ctxs[q] == ctxs[g]) return c->fail(GL_ERR_INVALID, "the same context appears twice");
+    if (cap_height > log_n + rate_bits) return c->fail(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len())");
+    if ((1ULL << cap_height) < n_ctx) return c->fail(GL_ERR_INVALID, "cap_height too small: every context must own at least one whole cap subtree");
+    const uint64_t n = 1ULL << log_n, R = n << rate_bits, rows = R / n_ctx;
+    const uint32_t local_h = cap_height - log2u(n_ctx);
+    std::vector<uint64_t> leaves(R * n_cols), digests(8 * (R - (1ULL << cap_height)) + 4);
+    if (glo_commit(cols, n_cols, log_n, rate_bits, cap_height, input_is_coeffs, nullptr, leaves.data(), digests.data(), out_cap, nullptr))
+        return c->fail(GL_ERR_INVALID, "oracle rejected the shape");
+    const uint64_t dig_per = 8 * (rows - (1ULL << local_h));
+    for (uint32_t g = 0; g < n_ctx; g++) {
+        auto t = std::make_unique<Tree>();
+        t->n_leaves = rows; t->leaf_len = n_cols; t->cap_height = local_h;
+        t->leaves.assign(leaves.begin() + g * rows * n_cols, leaves.begin() + (g + 1) * rows * n_cols);
+        t->digests.assign(digests.begin() + g * dig_per, digests.begin() + (g + 1) * dig_per);
+        t->cap.assign(out_cap + g * (4ULL << local_h), out_cap + (g + 1) * (4ULL << local_h));
+        out_trees[g] = ctxs[g]->next;
+        ctxs[g]->trees[ctxs[g]->next++] = std::move(t);
+    }
+    return GL_OK;
+}
+
 static int new_tree(gl_ctx* c, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t cap_height, uint64_t* out_digests, uint64_t* out_cap,
                     gl_handle* out_tree) {
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) return c->fail(GL_ERR_INVALID, "n_leaves must be a power of two");

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -500,6 +501,39 @@ static void test_concurrent_contexts() {
     for (int t = 0; t < T; t++) CHECK(bad[t] == 0, "thread %d: %d mismatches", t, bad[t]);
 }
 
+// from_values_multi: n contexts (all on device 0 here), the batch as shard trees under one cap
+static void test_commit_multi() {
+    const unsigned cfgs[][5] = {{2, 8, 20, 1, 1}, {4, 10, 135, 3, 4}, {8, 7, 9, 3, 3}};
+    for (auto& cfg : cfgs) {
+        const unsigned world = cfg[0], log_n = cfg[1], c = cfg[2], r = cfg[3], h = cfg[4];
+        const size_t n = size_t(1) << log_n, R = n << r;
+        std::vector<std::unique_ptr<Context>> own;
+        std::vector<Context*> ctxs;
+        for (unsigned k = 0; k < world; k++) { own.push_back(std::make_unique<Context>(0)); ctxs.push_back(own.back().get()); }
+        auto cols = splitmix_columns(800 + world, c, n);
+        OracleCommit ref = oracle_commit(cols, log_n, r, h, 0);
+        auto sharded = PolynomialBatch::from_values_multi(ctxs, as_values(cols), r, false, h);
+        CHECK(sharded.cap.flatten() == ref.cap, "multi: cap differs (world %u)", world);
+        CHECK(sharded.shards.size() == world && sharded.rows_per_shard() == R / world, "multi: shard shape");
+        bool ok = true;
+        for (size_t i = 0; i < R; i += R / 7 + 1) {
+            auto row = sharded.get(i);
+            ok &= std::memcmp(row.data(), ref.leaves.data() + i * c, 8 * c) == 0 && verify_path(row, i, sharded.prove(i), sharded.cap);
+        }
+        CHECK(ok, "multi: rows / paths (world %u)", world);
+        size_t off = 0;
+        ok = true;
+        for (auto& t : sharded.shards) {
+            const auto& d = t.digests();
+            ok &= d.empty() || std::memcmp(d[0].elements.data(), ref.digests.data() + off, 32 * d.size()) == 0;
+            off += 4 * d.size();
+        }
+        CHECK(ok && off == ref.digests.size(), "multi: digests (world %u)", world);
+        CHECK(panics_with("twice", [&] { PolynomialBatch::from_values_multi({ctxs[0], ctxs[0]}, as_values(cols), r, false, h); }), "same context twice must panic");
+        CHECK(panics_with("cap_height too small", [&] { PolynomialBatch::from_values_multi(ctxs, as_values(cols), r, false, 0); }), "cap_height < log2(world) must panic");
+    }
+}
+
 int main(int argc, char** argv) {
     bool expect_no_device = false;
     const char* golden_path = nullptr;
@@ -533,6 +567,8 @@ int main(int argc, char** argv) {
         std::printf("prove_openings: %d checks, %d failed\n", g_checks, g_fail);
         test_concurrent_contexts();
         std::printf("concurrent contexts: %d checks, %d failed\n", g_checks, g_fail);
+        test_commit_multi();
+        std::printf("commit_multi: %d checks, %d failed\n", g_checks, g_fail);
     } catch (const std::exception& e) {
         std::printf("FAIL: unexpected exception: %s\n", e.what());
         return 2;
