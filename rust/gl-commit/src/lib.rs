@@ -197,6 +197,53 @@ impl Context {
     }
 }
 
+/// `PolynomialBatch::from_values / from_coeffs` on several GPUs from this one process (`gl_commit_multi`): one context per
+/// device.  Returns the cap of the whole batch and one shard tree per context; leaf row `i` lives in
+/// `shards[i / rows_per_shard]` at local index `i % rows_per_shard`, and `prove` there is `MerkleTree::prove(i)`.
+pub fn commit_multi<'c>(
+    ctxs: &[&'c Context],
+    cols: &[&[u64]],
+    rate_bits: usize,
+    cap_height: usize,
+    input_is_coeffs: bool,
+) -> Result<(Vec<HashOut>, Vec<DeviceTree<'c>>), Error> {
+    let first = *ctxs.first().ok_or_else(|| Error::Invalid("no contexts".into()))?;
+    let n = cols.first().map(|c| c.len()).ok_or_else(|| Error::Invalid("empty polynomial batch".into()))?;
+    if cols.iter().any(|c| c.len() != n) {
+        return Err(Error::Invalid("Polynomial degrees inconsistent".into()));
+    }
+    if n == 0 || !n.is_power_of_two() {
+        return Err(Error::Invalid("polynomial length must be a power of two".into()));
+    }
+    if cap_height > 40 {
+        return Err(Error::Invalid(format!("cap_height={cap_height} should be at most log2(leaves.len())")));
+    }
+    let raw: Vec<*mut ffi::gl_ctx> = ctxs.iter().map(|c| c.raw).collect();
+    let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
+    let mut cap = vec![[0u64; 4]; 1 << cap_height];
+    let mut handles = vec![0 as ffi::gl_handle; ctxs.len()];
+    first.check(unsafe {
+        ffi::gl_commit_multi(
+            raw.as_ptr(),
+            raw.len() as u32,
+            ptrs.as_ptr(),
+            cols.len() as u32,
+            n.trailing_zeros(),
+            rate_bits as u32,
+            cap_height as u32,
+            input_is_coeffs as c_int,
+            cap.as_mut_ptr() as *mut u64,
+            handles.as_mut_ptr(),
+        )
+    })?;
+    let per = cap.len() / ctxs.len();
+    let mut shards = Vec::with_capacity(ctxs.len());
+    for (g, (&ctx, &h)) in ctxs.iter().zip(handles.iter()).enumerate() {
+        shards.push(DeviceTree::adopt(ctx, h, cap[g * per..(g + 1) * per].to_vec())?);
+    }
+    Ok((cap, shards))
+}
+
 impl Drop for Context {
     fn drop(&mut self) {
         unsafe { ffi::gl_ctx_destroy(self.raw) }
