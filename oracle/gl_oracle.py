@@ -19,6 +19,9 @@ Parity pinning status
   /root/reference/src/common/poseidon2/poseidon2_goldilocks.rs:190-211 (tests/golden/poseidon_kat.json).
 * Field constants: PINNED (/root/reference/src/p3/mod.rs:55, src/p3/extension.rs:149,155,
   src/p3/serde/two_adic.rs:19,35,66).
+* Sponge absorb mode: corroborated (not pinned) by the reference's implementation of plonky2's PlonkyPermutation trait
+  (/root/reference/src/common/poseidon2/poseidon2.rs:528-565: set_elt / set_from_slice / set_from_iter overwrite lanes, squeeze is
+  state[..RATE]); plonky2's generic hash_n_to_hash_no_pad / compress are called through that interface at :575-581.
 * LDE order, sponge mode, digest layout, FRI fold: "parity unpinned" — the reference tree holds no golden
   vectors for them and cannot be run here (no Rust toolchain).  They are cross-checked by two independent
   restatements (this file vs oracle/gl_oracle.c) and by oracle-independent algebraic invariants
