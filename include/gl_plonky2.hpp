@@ -289,10 +289,30 @@ private:
 };
 
 /* ------------------------------------------------------------------------------------------------ FRI structures */
-struct FriConfig {                            /* plonky2 fri/mod.rs (reduction_strategy is resolved into FriParams) */
+/* plonky2 fri/reduction_strategies.rs · FriReductionStrategy (Fixed / ConstantArityBits; MinSize is a search over the latter's
+ * parameter and is not used by standard_recursion_config) */
+struct FriReductionStrategy {
+    enum Kind { Fixed, ConstantArityBits } kind = ConstantArityBits;
+    std::vector<size_t> fixed;                /* Fixed(arity_bits) */
+    size_t arity_bits = 4, final_poly_bits = 5;   /* ConstantArityBits(4, 5): standard_recursion_config */
+    std::vector<size_t> reduction_arity_bits(size_t degree_bits, size_t rate_bits, size_t cap_height, size_t /*num_queries*/) const {
+        if (kind == Fixed) return fixed;
+        std::vector<size_t> result;
+        while (degree_bits > final_poly_bits && degree_bits + rate_bits - arity_bits >= cap_height) {
+            result.push_back(arity_bits);
+            if (degree_bits < arity_bits) throw Panic("assertion failed: degree_bits >= *arity_bits");
+            degree_bits -= arity_bits;
+        }
+        return result;
+    }
+};
+struct FriParams;
+struct FriConfig {                            /* plonky2 fri/mod.rs; defaults = CircuitConfig::standard_recursion_config().fri_config */
     size_t rate_bits = 3, cap_height = 4;
     uint32_t proof_of_work_bits = 16;
+    FriReductionStrategy reduction_strategy;
     size_t num_query_rounds = 28;
+    inline FriParams fri_params(size_t degree_bits, bool hiding) const;
 };
 struct FriParams {
     FriConfig config;
@@ -301,7 +321,19 @@ struct FriParams {
     std::vector<size_t> reduction_arity_bits;
     size_t lde_bits() const { return degree_bits + config.rate_bits; }
     size_t lde_size() const { return size_t(1) << lde_bits(); }
+    size_t total_arities() const { size_t t = 0; for (size_t a : reduction_arity_bits) t += a; return t; }
+    size_t final_poly_bits() const { return degree_bits - total_arities(); }
+    size_t final_poly_len() const { return size_t(1) << final_poly_bits(); }
 };
+/* FriConfig::fri_params(degree_bits, hiding) */
+inline FriParams FriConfig::fri_params(size_t degree_bits, bool hiding) const {
+    FriParams p;
+    p.config = *this;
+    p.hiding = hiding;
+    p.degree_bits = degree_bits;
+    p.reduction_arity_bits = reduction_strategy.reduction_arity_bits(degree_bits, rate_bits, cap_height, num_query_rounds);
+    return p;
+}
 struct FriPolynomialInfo { size_t oracle_index, polynomial_index; };
 struct FriBatchInfo { Ext point; std::vector<FriPolynomialInfo> polynomials; };
 struct FriOracleInfo { size_t num_polys = 0; bool blinding = false; };

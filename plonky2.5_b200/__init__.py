@@ -8,8 +8,8 @@ repository root) or via importlib.
 from . import _lib  # noqa: F401
 from . import sharded  # noqa: F401
 from .api import (Challenger, Context, FriBatchInfo, FriParams, FriProofHead, GlError, MerkleCap, MerkleTree,  # noqa: F401
-                  PolynomialBatch, commit_multi, default_context, fri_committed_trees, fri_proof_of_work, fri_prover_query_rounds, prove_openings)
+                  PolynomialBatch, commit_multi, default_context, fri_committed_trees, fri_proof_of_work, fri_prover_query_rounds, prove_openings, reduction_arity_bits)
 from .build import build  # noqa: F401
 
 __all__ = ["Challenger", "Context", "FriBatchInfo", "FriParams", "FriProofHead", "GlError", "MerkleCap", "MerkleTree",
-           "PolynomialBatch", "commit_multi", "default_context", "fri_committed_trees", "fri_proof_of_work", "fri_prover_query_rounds", "prove_openings", "build"]
+           "PolynomialBatch", "commit_multi", "default_context", "fri_committed_trees", "fri_proof_of_work", "fri_prover_query_rounds", "prove_openings", "reduction_arity_bits", "build"]

@@ -368,6 +368,18 @@ class FriParams:
         self.reduction_arity_bits = list(reduction_arity_bits)
 
 
+def reduction_arity_bits(degree_bits: int, rate_bits: int, cap_height: int, arity_bits: int = 4, final_poly_bits: int = 5) -> List[int]:
+    """plonky2 fri/reduction_strategies.rs · FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits).reduction_arity_bits
+    (standard_recursion_config uses (4, 5): the wrapper circuit, degree_bits 16, folds 4, 4, 4 down to 16 coefficients)."""
+    out = []
+    while degree_bits > final_poly_bits and degree_bits + rate_bits - arity_bits >= cap_height:
+        out.append(arity_bits)
+        if degree_bits < arity_bits:
+            raise ValueError("assertion failed: degree_bits >= *arity_bits")
+        degree_bits -= arity_bits
+    return out
+
+
 def _fri_commit_phase(ctx: Context, fh: int, challenger, fri_params: FriParams):
     """the per-layer loop of fri_committed_trees on a device-resident FRI state (gl_fri handle)"""
     lib = ctx.lib

@@ -501,6 +501,23 @@ static void test_concurrent_contexts() {
     for (int t = 0; t < T; t++) CHECK(bad[t] == 0, "thread %d: %d mismatches", t, bad[t]);
 }
 
+// FriConfig::fri_params: the wrapper circuit (degree_bits 16, standard_recursion_config) folds 4, 4, 4 down to 16 coefficients
+// (SURVEY.md A.7); host arithmetic only
+static void test_fri_params() {
+    FriConfig cfg;
+    FriParams p = cfg.fri_params(16, false);
+    CHECK(p.reduction_arity_bits == std::vector<size_t>({4, 4, 4}) && p.final_poly_len() == 16 && p.lde_bits() == 19, "standard config, degree_bits 16");
+    CHECK(cfg.fri_params(5, false).reduction_arity_bits.empty(), "degree_bits <= final_poly_bits: no reduction");
+    CHECK(cfg.fri_params(12, false).reduction_arity_bits == std::vector<size_t>({4, 4}), "degree_bits 12");
+    FriConfig tall = cfg;
+    tall.cap_height = 14;                              // a layer must keep at least 2^cap_height leaves
+    CHECK(tall.fri_params(16, false).reduction_arity_bits == std::vector<size_t>({4}), "cap-limited reduction");
+    FriConfig fixed = cfg;
+    fixed.reduction_strategy.kind = FriReductionStrategy::Fixed;
+    fixed.reduction_strategy.fixed = {3, 2};
+    CHECK(fixed.fri_params(10, false).reduction_arity_bits == std::vector<size_t>({3, 2}), "Fixed strategy");
+}
+
 // from_values_multi: n contexts (all on device 0 here), the batch as shard trees under one cap
 static void test_commit_multi() {
     const unsigned cfgs[][5] = {{2, 8, 20, 1, 1}, {4, 10, 135, 3, 4}, {8, 7, 9, 3, 3}};
@@ -569,6 +586,8 @@ int main(int argc, char** argv) {
         std::printf("concurrent contexts: %d checks, %d failed\n", g_checks, g_fail);
         test_commit_multi();
         std::printf("commit_multi: %d checks, %d failed\n", g_checks, g_fail);
+        test_fri_params();
+        std::printf("fri_params: %d checks, %d failed\n", g_checks, g_fail);
     } catch (const std::exception& e) {
         std::printf("FAIL: unexpected exception: %s\n", e.what());
         return 2;

@@ -108,3 +108,16 @@ def test_commit_multi_rejects_null_without_touching_a_device():
     from plonky25_b200 import _lib
     lib = _lib.load()
     assert lib.gl_commit_multi(None, 2, None, 4, 3, 1, 1, 0, None, None) == _lib.GL_ERR_INVALID
+
+
+def test_reduction_arity_bits_mirrors_match_the_oracle():
+    """FriReductionStrategy::ConstantArityBits in the Python mirror == the oracle's restatement (SURVEY A.7: [4, 4, 4] for the wrapper)"""
+    import plonky25_b200 as g
+    import gl_oracle as o
+    assert g.reduction_arity_bits(16, 3, 4) == [4, 4, 4]
+    for degree_bits in range(0, 24):
+        for rate_bits in (1, 3):
+            for cap_height in (0, 4, 14):
+                for ab, fp in ((4, 5), (3, 2), (1, 0)):
+                    assert g.reduction_arity_bits(degree_bits, rate_bits, cap_height, ab, fp) == \
+                        o.reduction_arity_bits_constant(ab, fp, degree_bits, rate_bits, cap_height)
