@@ -103,6 +103,27 @@ def test_cpp_host_mirror_host_logic_on_abi_double(tmp_path):
     assert "glo_" not in nm, "libgl_commit.so must not reference the oracle"
 
 
+def test_cpp_host_mirror_under_sanitizers(tmp_path):
+    """the header's host logic (handle ownership, moves, query-round assembly) under AddressSanitizer + UBSan + LeakSanitizer, on the
+    ABI double: every device handle a mirror object owns must be released exactly once"""
+    from oracle_c import build_oracle
+    ora = build_oracle()
+    exe = str(tmp_path / "host_mirror_asan")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", os.path.join(ROOT, "include"),
+                        SRC, os.path.join(ROOT, "tests", "cpp", "abi_test_double.cpp"), "-o", exe, "-L", os.path.dirname(ora), "-lgl_oracle",
+                        "-Wl,-rpath," + os.path.dirname(ora), "-pthread"], capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + r.stderr[-300:])
+    gold = tmp_path / "openings_fri.txt"
+    _flatten_golden(str(gold))
+    env["ASAN_OPTIONS"] = "detect_leaks=1"
+    r = subprocess.run([exe, "--golden", str(gold)], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "ALL OK" in r.stdout and "ERROR" not in r.stderr and "runtime error" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def _cxx(args):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     env = dict(os.environ)
