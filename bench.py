@@ -78,6 +78,7 @@ def cpu_commit_time(oc, log_n, cols, r, h, seed=1):
 def cpu_baseline(a, repeats=1):
     from oracle_c import OracleC
     oc = OracleC()
+    oc.set_threads(host_threads())
     threads = oc.num_threads()
     log_n = min(a.cpu_sample_log_n, a.log_n)
     best, stages = None, None
@@ -105,24 +106,46 @@ def cpu_baseline(a, repeats=1):
             "stage_s": {k: round(v, 3) for k, v in zip(("ifft", "lde_fft", "transpose", "merkle"), stages)}}
 
 
+def host_threads():
+    """threads the CPU arm may use: every core this process is allowed on.  torchrun exports OMP_NUM_THREADS=1 to its children;
+    that setting is for GPU ranks and must not throttle the CPU baseline, so the oracle's thread count is set explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(a):
-    """--impl reference: the CPU restatement on all host threads, bounded sample per step."""
+    """--impl reference: the CPU restatement on all host threads, bounded sample per step (rank 0 only; the whole run is sized to
+    end within ~2 minutes whatever the core count)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle_c import OracleC
     oc = OracleC()
+    threads = host_threads()
+    oc.set_threads(threads)
     threads = oc.num_threads()
-    log_n = min(a.cpu_sample_log_n, a.log_n)
-    for _ in range(a.warmup):
-        cpu_commit_time(oc, min(log_n, 12), a.cols, a.rate_bits, a.cap_height)     # warm-up on a small case (page-in, OpenMP pool)
+    # size the sample from a probe: one 2^13 commit is timed, cost is ~linear in rows, and the largest sample <= --cpu-sample-log-n
+    # whose (warmup + steps) fits the time budget is used
+    probe_log_n = min(13, a.log_n)
+    cpu_commit_time(oc, min(10, a.log_n), a.cols, a.rate_bits, a.cap_height)          # page-in, OpenMP pool
+    t_probe, _ = cpu_commit_time(oc, probe_log_n, a.cols, a.rate_bits, a.cap_height)
+    budget_s = float(os.environ.get("GL_REF_BUDGET_S", "100"))
+    log_n = probe_log_n
+    while log_n < min(a.cpu_sample_log_n, a.log_n) and t_probe * (1 << (log_n + 1 - probe_log_n)) * (a.steps + min(a.warmup, 1)) <= budget_s:
+        log_n += 1
+    for _ in range(min(a.warmup, 1)):                                                   # one full-size warm-up, the rest on a small case
+        cpu_commit_time(oc, log_n, a.cols, a.rate_bits, a.cap_height)
+    for _ in range(max(a.warmup - 1, 0)):
+        cpu_commit_time(oc, min(log_n, 12), a.cols, a.rate_bits, a.cap_height)
     t0 = time.perf_counter()
     for s in range(a.steps):
         cpu_commit_time(oc, log_n, a.cols, a.rate_bits, a.cap_height, seed=s + 1)
     dt = time.perf_counter() - t0
     val = a.steps * (a.cols << log_n) / dt / 1e6
     sample = (f"each step = one commit of 2^{log_n} x {a.cols} (1/{1 << (a.log_n - log_n)} of the workload's rows; throughput in "
-              "elements/s is what is compared), oracle/gl_oracle.c with OpenMP")
+              f"elements/s is what is compared), oracle/gl_oracle.c with {threads} OpenMP threads")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 (Goldilocks field)", "data": "synthetic",
@@ -271,6 +294,10 @@ def main():
     ms_per_step = dev_ms / a.steps
     value = cols * n / (ms_per_step * 1e-3) / 1e6
     cap_dev = cap.copy()
+    # parity: the cap this run produced against the oracle's golden cap for the same synthetic input (tests/golden/headline_*.json,
+    # plain JSON — the oracle itself is not executed here).  A mismatch fails the run: a fast wrong commit is not a result.
+    import headline
+    parity = headline.parity_block(cap_dev, log_n, cols, r, h, seed=1)
 
     # ---- e2e: the C-ABI call a Rust shim would make, host buffers in, cap out, every step --------------------------
     e2e = None
@@ -312,7 +339,7 @@ def main():
             hb = torch.tensor([h2d], dtype=torch.int64, device=dev)
             dist.all_reduce(hb)
             h2d = int(hb.item())
-        assert np.array_equal(cap, cap_dev), "host-buffer path and device-resident path disagree on the Merkle cap"
+        parity["e2e_cap_equals_device_cap"] = bool(np.array_equal(cap, cap_dev))
         e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
@@ -329,12 +356,17 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (leaf hashing), live CUDA-event time from the context's stage events -------
+    # The BINDING line leads: this kernel is limited by the SM issue port (integer + fp64 work on a 64-bit prime field, no
+    # contraction), so `roofline` = executed warp-instructions/s against one warp-instruction per sub-partition per clock.  Its
+    # numerator is EXECUTED instructions (ncu smsp__inst_executed per permutation x the live permutation rate): it measures how full
+    # the issue port is, not how lean the code is — `imad_wide_floor` is the algorithmic floor (the 1652 IMAD.WIDE.U32 of the 118
+    # S-boxes at the measured multiplier rate) and `hbm` the contractual memory line (which does not bind).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     R = n << r
     rows_local = R // world
     leaf_ms = stage_acc.get("leaf_hash", 0.0) / a.steps
@@ -343,28 +375,50 @@ def main():
     roof = None
     if leaf_ms > 0:
         ach = alg_bytes / (leaf_ms * 1e-3) / 1e9
-        roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": round(ach, 2), "peak": peak_gbs, "unit": "GB/s",
-                "frac": round(ach / peak_gbs, 5), "traffic": None, "peak_source": peak_src, "ms_per_launch": round(leaf_ms, 3),
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "hashing is bound by the SM instruction-issue/dispatch port, not HBM (DESIGN.md §4): `issue` is the binding roofline",
-                "issue": None}
+        hbm = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak_gbs, "unit": "GB/s", "frac": round(ach / peak_gbs, 5),
+               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "traffic": None,
+               "note": "contractual memory line; does not bind (DESIGN.md §4)"}
+        roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "hbm", "achieved": hbm["achieved"], "peak": peak_gbs, "unit": "GB/s",
+                "frac": hbm["frac"], "traffic": None, "ms_per_launch": round(leaf_ms, 3), "hbm": hbm}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "leaf_hash_profile.json")))
             if prof.get("cols") == cols:
-                # instructions per permutation are data-independent (branch-free code): ncu's smsp__inst_executed of one
-                # launch / its permutations; the peak is one warp instruction per SM sub-partition per clock
                 ipp = prof["warp_inst_per_launch"] / (prof["rows"] * ((cols + 7) // 8) / 32)
                 sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-                peak_issue = 148 * 4 * sm_mhz * 1e6
-                ach_issue = perms_leaf / 32 * ipp / (leaf_ms * 1e-3)
-                roof["issue"] = {"achieved_warp_inst_per_s": round(ach_issue, 1), "peak_warp_inst_per_s": peak_issue,
-                                 "frac": round(ach_issue / peak_issue, 4), "warp_inst_per_permutation": round(ipp, 1),
-                                 "permutations_per_s": round(perms_leaf / (leaf_ms * 1e-3), 1), "sm_mhz": sm_mhz,
-                                 "source": prof.get("source")}
-            if prof.get("rows") == rows_local and prof.get("cols") == cols:
-                roof["traffic"] = prof["dram_bytes_per_launch"]
+                n_smsp = 148 * 4
+                peak_issue = n_smsp * sm_mhz * 1e6
+                perm_rate = perms_leaf / (leaf_ms * 1e-3)
+                ach_issue = perm_rate / 32 * ipp
+                clk_per_warp_perm = n_smsp * sm_mhz * 1e6 / (perm_rate / 32)
+                wide_per_perm, wide_rate = prof.get("imad_wide_per_permutation", 1652), prof.get("imad_wide_warp_inst_per_clk_per_smsp", 0.175)
+                if prof.get("rows") == rows_local:
+                    hbm["traffic"] = prof["dram_bytes_per_launch"]
+                roof = {"kernel": "merkle::leaf_hash_kernel", "bound": "sm-issue", "achieved": round(ach_issue, 1), "peak": peak_issue,
+                        "unit": "warp-inst/s", "frac": round(ach_issue / peak_issue, 4), "traffic": hbm["traffic"],
+                        "ms_per_launch": round(leaf_ms, 3), "permutations_per_s": round(perm_rate, 1),
+                        "warp_inst_per_permutation": round(ipp, 1), "sm_mhz": sm_mhz,
+                        "numerator": "executed warp instructions (ncu smsp__inst_executed / permutation x live permutation rate): issue-port "
+                                     "occupancy, not efficiency",
+                        "peak_source": "148 SMs x 4 sub-partitions x 1 warp-inst/clk x SM clock sampled during the run",
+                        "profile": prof.get("source"),
+                        "imad_wide_floor": {"frac": round(wide_per_perm / wide_rate / clk_per_warp_perm, 4),
+                                            "imad_wide_per_permutation": wide_per_perm, "warp_inst_per_clk_per_smsp": wide_rate,
+                                            "clk_per_warp_permutation": round(clk_per_warp_perm, 1),
+                                            "note": "algorithmic floor: 118 S-boxes x 14 IMAD.WIDE.U32 at the measured multiplier rate "
+                                                    "(profiles/r01_ubench2_issue_port.txt)"},
+                        "hbm": hbm}
         except (OSError, KeyError):
             pass
+        # the NTT passes (second kernel by time) against the HBM line: every pass reads and writes the matrix once
+        pitch = (cols // world + 7) // 8 * 8 if world > 1 else (cols + 7) // 8 * 8
+        n_pass = -(-log_n // 10) if log_n >= 3 else 1
+        for stage, n_ntt in (("intt", 1), ("lde", 1 << r)):
+            ms_st = stage_acc.get(stage, 0.0) / a.steps
+            if ms_st > 0:
+                b = 16 * n * pitch * n_pass * n_ntt
+                roof.setdefault("ntt", {})[stage] = {"bound": "hbm", "achieved": round(b / (ms_st * 1e-3) / 1e9, 1), "peak": peak_gbs, "unit": "GB/s",
+                                                     "frac": round(b / (ms_st * 1e-3) / 1e9 / peak_gbs, 4), "algorithmic_bytes": b,
+                                                     "launches": n_pass * n_ntt, "ms": round(ms_st, 3)}
 
     cpu = None if (a.no_cpu_baseline or world > 1) else cpu_baseline(a)   # rank 0 at N=1 only
 
@@ -378,10 +432,12 @@ def main():
                        "l2": "inputs (%.2f GB) and leaves (%.2f GB) exceed the 126 MB L2; no flush needed" % (cols * n * 8 / 1e9, R * cols * 8 / 1e9),
                        "permutations_per_step": perms_per_commit(log_n, cols, r, h)},
             "stage_ms": {k: round(v / a.steps, 4) for k, v in stage_acc.items()},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity["match"] is False or parity.get("e2e_cap_equals_device_cap") is False:
+        raise SystemExit("PARITY MISMATCH: the Merkle cap differs from the oracle's golden (see the `parity` object)")
 
 
 if __name__ == "__main__":

@@ -200,6 +200,12 @@ int gl_dev_repack(gl_ctx* ctx, const uint64_t* d_src, uint32_t src_pitch, uint32
 int gl_dev_merkle(gl_ctx* ctx, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch,
                   uint32_t cap_height, uint64_t* d_digests, uint64_t* out_cap);
 
+/* plain device memory + copies for hosts without a CUDA binding of their own (tests, the C++ tools): words are uint64_t */
+int gl_dev_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr);
+int gl_dev_free(gl_ctx* ctx, uint64_t* ptr);
+int gl_dev_upload(gl_ctx* ctx, const uint64_t* host_src, uint64_t* d_dst, uint64_t words);
+int gl_dev_download(gl_ctx* ctx, const uint64_t* d_src, uint64_t* host_dst, uint64_t words);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
 enum {
     GL_STAGE_H2D = 0, GL_STAGE_TRANSPOSE = 1, GL_STAGE_INTT = 2, GL_STAGE_LDE = 3, GL_STAGE_LEAF_HASH = 4,

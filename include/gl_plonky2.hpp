@@ -166,7 +166,9 @@ public:
     /* the same over packed row-major leaves (no Vec<Vec<F>> allocations) */
     static MerkleTree from_flat(const F* leaves, size_t n_leaves, size_t leaf_len, size_t cap_height, Context* ctx = nullptr) {
         Context& c = ctx_or_default(ctx);
-        if (cap_height > 40) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
+        /* upstream's assert, checked before the cap is sized by 2^cap_height */
+        if (cap_height >= 64 || n_leaves == 0 || (size_t(1) << cap_height) > n_leaves)
+            throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
         MerkleCap cap;
         cap.hashes.resize(size_t(1) << cap_height);
         gl_handle h = 0;
@@ -364,8 +366,12 @@ struct FriState {
 inline std::pair<std::vector<MerkleTree>, PolynomialCoeffsExt> commit_phase(Context& ctx, gl_handle fri, Challenger& challenger,
                                                                             const FriParams& p) {
     std::vector<MerkleTree> trees;
-    if (p.config.cap_height > 40) throw Panic("cap_height should be at most log2(leaves.len())");
+    uint64_t cur = 0;
+    ctx.check(gl_fri_read(ctx.raw(), fri, nullptr, nullptr, &cur));
     for (size_t arity_bits : p.reduction_arity_bits) {
+        cur = arity_bits < 64 ? cur >> arity_bits : 0;   /* leaves of this layer: MerkleTree::new's assert, before the cap is sized */
+        if (p.config.cap_height > 31 || (cur != 0 && (uint64_t(1) << p.config.cap_height) > cur))   /* cur == 0: the library reports the arity */
+            throw Panic("cap_height=" + std::to_string(p.config.cap_height) + " should be at most log2(leaves.len())");
         MerkleCap cap;
         cap.hashes.resize(size_t(1) << p.config.cap_height);
         gl_handle th = 0;
@@ -439,9 +445,10 @@ inline std::vector<FriQueryRound> fri_prover_query_rounds(const std::vector<cons
             const std::vector<F>& leaf = opened[q].first;                  /* unflatten: arity extension elements */
             if (leaf.size() != 2 * arity) throw Panic("fri_prover_query_rounds: commit-phase leaf is not arity extension elements");
             FriQueryStep step;
-            const size_t skip = cur[q] & (arity - 1);                      /* evals.remove(x_index & (arity - 1)) */
-            for (size_t k = 0; k < arity; k++)
-                if (k != skip) step.evals.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});
+            /* evals = unflatten(tree.get(x_index >> arity_bits)): ALL arity elements — validate_shape wants evals.len() == arity and
+             * the verifier reads evals[x_index & (arity - 1)]; only FriProof::compress drops the queried element */
+            step.evals.reserve(arity);
+            for (size_t k = 0; k < arity; k++) step.evals.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});
             step.merkle_proof = std::move(opened[q].second);
             out[q].steps.push_back(std::move(step));
         }
@@ -583,7 +590,11 @@ public:
         if (values.empty()) throw Panic("PolynomialBatch: empty polynomial batch");
         const size_t n = values[0].len();
         if (n == 0 || (n & (n - 1))) throw Panic("PolynomialBatch: polynomial length must be a power of two");
-        if (cap_height > 40) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
+        {   /* upstream's assert, checked before the cap is sized by 2^cap_height */
+            size_t lg = 0;
+            while ((size_t(1) << lg) < n) lg++;
+            if (cap_height > lg + rate_bits) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
+        }
         std::vector<const uint64_t*> cols;
         for (const auto& v : values) {
             if (v.len() != n) throw Panic("Polynomial degrees inconsistent");
@@ -615,10 +626,11 @@ private:
         if (blinding) throw Panic("blinding (zero_knowledge) is not on the GPU path: the reference runs with zk off (src/p3/mod.rs:231)");
         if (cols.empty()) throw Panic("PolynomialBatch: empty polynomial batch");
         if (n == 0 || (n & (n - 1))) throw Panic("PolynomialBatch: polynomial length must be a power of two");
-        if (cap_height > 40) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
         Context& c = ctx_or_default(ctx);
         size_t log_n = 0;
         while ((size_t(1) << log_n) < n) log_n++;
+        /* upstream's assert, checked before the cap is sized by 2^cap_height */
+        if (cap_height > log_n + rate_bits) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
         MerkleCap cap;
         cap.hashes.resize(size_t(1) << cap_height);
         gl_handle h = 0;

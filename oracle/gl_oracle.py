@@ -612,7 +612,10 @@ def prove_openings_lde(final_poly: Sequence[Ext], rate_bits: int):
 
 def fri_prover_query_rounds(initial_trees: Sequence[MerkleTree], trees: Sequence[MerkleTree], challenger: Challenger,
                             n_query_rounds: int, reduction_arity_bits: Sequence[int], lde_size: int):
-    """plonky2/src/fri/prover.rs · fri_prover_query_rounds / fri_prover_query_round (restated from memory of upstream @ 3de92d9)."""
+    """plonky2/src/fri/prover.rs · fri_prover_query_rounds / fri_prover_query_round (restated from memory of upstream @ 3de92d9):
+    per step `evals = unflatten(tree.get(x_index >> arity_bits))` — the whole coset, `arity` extension elements; the verifier
+    (fri/verifier.rs · fri_verifier_query_round) reads evals[x_index & (arity-1)] and Merkle-verifies flatten(evals), and
+    validate_shape requires evals.len() == arity."""
     rounds = []
     for _ in range(n_query_rounds):
         x_index = challenger.get_challenge() % lde_size
@@ -621,8 +624,8 @@ def fri_prover_query_rounds(initial_trees: Sequence[MerkleTree], trees: Sequence
         for arity_bits, tree in zip(reduction_arity_bits, trees):
             arity = 1 << arity_bits
             flat = tree.get(x >> arity_bits)
-            evals = [(flat[2 * i], flat[2 * i + 1]) for i in range(arity)]
-            del evals[x & (arity - 1)]
+            evals = [(flat[2 * i], flat[2 * i + 1]) for i in range(arity)]   # unflatten(tree.get(..)): ALL arity elements; dropping the
+            # queried one is FriProof::compress's job (fri/proof.rs), and decompress re-inserts it before the verifier runs
             rnd["steps"].append({"evals": evals, "merkle_proof": tree.prove(x >> arity_bits)})
             x >>= arity_bits
         rounds.append(rnd)

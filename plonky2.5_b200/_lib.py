@@ -67,6 +67,10 @@ SIGNATURES = {
     "gl_dev_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "gl_dev_ipc_close": (c_int, [c_void_p, c_void_p]),
     "gl_dev_ipc_free": (c_int, [c_void_p, c_void_p]),
+    "gl_dev_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p)]),
+    "gl_dev_free": (c_int, [c_void_p, c_void_p]),
+    "gl_dev_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64]),
+    "gl_dev_download": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64]),
     "gl_dev_repack": (c_int, [c_void_p, c_void_p, c_uint32, c_uint32, c_uint64, c_void_p, c_uint32, c_uint32]),
     "gl_dev_merkle": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p]),
     "gl_ctx_stage_times": (c_int, [c_void_p, POINTER(c_float), POINTER(c_uint32)]),

@@ -144,7 +144,9 @@ class MerkleTree:
         if lv.ndim != 2:
             raise ValueError("leaves must be a 2-D array [n_leaves][leaf_len]")
         n, ll = lv.shape
-        cap = np.zeros((1 << cap_height) * 4 if cap_height < 40 else 0, dtype=np.uint64)
+        if n == 0 or cap_height > n.bit_length() - 1:   # upstream's assert, checked BEFORE sizing the cap buffer by 2^cap_height
+            raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={max(n.bit_length() - 1, 0)}")
+        cap = np.zeros(4 << cap_height, dtype=np.uint64)
         dig = None
         if copy_back and n >= (1 << cap_height):
             dig = np.zeros((2 * (n - (1 << cap_height)), 4), dtype=np.uint64)
@@ -236,8 +238,8 @@ class PolynomialBatch:
         n_cols, n = len(cols), 1 << log_n
         rows = n << rate_bits
         ptrs = (c_void_p * n_cols)(*[c.ctypes.data for c in cols])
-        if cap_height > 40:
-            raise ValueError("cap_height should be at most log2(leaves.len())")
+        if cap_height > log_n + rate_bits:               # upstream's assert, checked BEFORE sizing the cap buffer by 2^cap_height
+            raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={log_n + rate_bits}")
         cap = np.zeros(4 << cap_height, dtype=np.uint64)
         oc = ol = od = None
         if copy_back:
@@ -283,8 +285,8 @@ def commit_multi(ctxs: Sequence[Context], values, rate_bits: int, cap_height: in
     sharded for the LDE, leaf ranges hashed per context.  Returns (cap, shard trees); leaf row i of the batch lives in
     trees[i // (R // len(ctxs))] at local index i % (R // len(ctxs)), and `.prove` there is MerkleTree::prove(i)."""
     cols, log_n = PolynomialBatch._cols(values)
-    if cap_height > 40:
-        raise ValueError("cap_height should be at most log2(leaves.len())")
+    if cap_height > log_n + rate_bits:
+        raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={log_n + rate_bits}")
     lib = ctxs[0].lib
     hs = (c_void_p * len(ctxs))(*[c.handle for c in ctxs])
     ptrs = (c_void_p * len(cols))(*[c.ctypes.data for c in cols])
@@ -384,7 +386,13 @@ def _fri_commit_phase(ctx: Context, fh: int, challenger, fri_params: FriParams):
     """the per-layer loop of fri_committed_trees on a device-resident FRI state (gl_fri handle)"""
     lib = ctx.lib
     trees = []
+    cur = c_uint64()
+    _check(ctx, lib.gl_fri_read(ctx.handle, fh, None, None, byref(cur)))
+    cur = int(cur.value)
     for arity_bits in fri_params.reduction_arity_bits:
+        cur >>= arity_bits                      # leaves of this layer; MerkleTree::new's assert before the cap is sized
+        if fri_params.cap_height > (cur.bit_length() - 1 if cur else 31):   # cur == 0: the library reports "arity larger than the codeword"
+            raise ValueError(f"cap_height={fri_params.cap_height} should be at most log2(leaves.len())={max(cur.bit_length() - 1, 0)}")
         cap = np.zeros(4 << fri_params.cap_height, dtype=np.uint64)
         th = c_uint64()
         _check(ctx, lib.gl_fri_commit_layer(ctx.handle, fh, arity_bits, None, None, _ptr(cap), byref(th)))
@@ -496,9 +504,9 @@ def fri_prover_query_rounds(initial_merkle_trees: Sequence[MerkleTree], trees: S
                             fri_params: FriParams, lde_size: Optional[int] = None) -> List[dict]:
     """plonky2 fri/prover.rs · fri_prover_query_rounds / fri_prover_query_round: per round x_index = challenge mod lde_size;
     initial_trees_proof = [(tree.get(x), tree.prove(x))] for every initial oracle; per commit-phase layer the coset evaluations
-    (the leaf x >> arity_bits with the queried element removed) and the Merkle proof of that leaf.  All indices of a tree are
+    (the whole leaf x >> arity_bits = `arity` extension elements, as upstream's FriQueryStep holds them) and its Merkle proof.  All indices of a tree are
     opened in one gl_tree_open_batch call.  Returns one dict per round:
-    {"x_index", "initial_trees_proof": [(row, siblings)], "steps": [{"evals": [arity-1][2], "merkle_proof": siblings}]}."""
+    {"x_index", "initial_trees_proof": [(row, siblings)], "steps": [{"evals": [arity][2], "merkle_proof": siblings}]}."""
     n = int(lde_size if lde_size is not None else initial_merkle_trees[0].n_leaves)
     xs = [int(challenger.get_challenge()) % n for _ in range(n_query_rounds)]
     init = [t.open_batch(xs) for t in initial_merkle_trees]
@@ -512,9 +520,8 @@ def fri_prover_query_rounds(initial_merkle_trees: Sequence[MerkleTree], trees: S
     for q, x in enumerate(xs):
         rnd = {"x_index": x, "initial_trees_proof": [(rows[q], sib[q]) for rows, sib in init], "steps": []}
         for arity_bits, rows, sib, idx in steps:
-            evals = rows[q].reshape(-1, 2)
-            keep = np.ones(1 << arity_bits, dtype=bool)
-            keep[idx[q] & ((1 << arity_bits) - 1)] = False        # evals.remove(x_index & (arity - 1))
-            rnd["steps"].append({"evals": evals[keep], "merkle_proof": sib[q]})
+            # evals = unflatten(tree.get(x_index >> arity_bits)): all `arity` elements of the coset (only FriProof::compress drops
+            # the queried one; the verifier reads evals[x_index & (arity - 1)] and Merkle-verifies flatten(evals))
+            rnd["steps"].append({"evals": rows[q].reshape(-1, 2).copy(), "merkle_proof": sib[q]})
         out.append(rnd)
     return out

@@ -22,12 +22,23 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(HERE, ".libgl_commit.srchash")   # travels with the .so (git-ignored, not gpurun-ignored)
+
+
+def source_hash() -> str:
+    """sha256 over the flags and every source the library is built from: the build is skipped only when the .so on disk was built
+    from exactly these bytes (mtimes mean nothing on a fresh checkout or a copied snapshot)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "gl_commit.h")]:
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "gl_commit.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(STAMP).read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -40,6 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)   # the image's CC wrapper is not a valid nvcc host compiler choice
     subprocess.run(cmd, check=True, env=env)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

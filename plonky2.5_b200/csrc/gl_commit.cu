@@ -172,6 +172,8 @@ struct gl_ctx {
     std::map<uint32_t, std::unique_ptr<DevBuf>> roots;                       // log_n -> W
     std::map<uint32_t, std::unique_ptr<DevBuf>> pass_roots;                  // a -> w_{2^a}^e, e < 7*2^a/8 (round twiddles)
     std::map<uint64_t, std::unique_ptr<std::vector<CosetTable>>> lde_tables;  // (log_n, rate_bits) -> per coset
+    std::map<std::pair<uint64_t, uint32_t>, std::unique_ptr<CosetTable>> coset_cache;   // (shift, log_len) -> g^j: FRI layers / final-poly LDE
+    size_t coset_cache_words = 0;
     DevBuf in_stage, vals, scratch;
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
     std::map<gl_handle, std::unique_ptr<Fri>> fris;
@@ -238,15 +240,38 @@ const uint64_t* get_pass_roots(gl_ctx* c, uint32_t a) {
     return p;
 }
 
+// F[j] = g^j, j < 2^log_n, filled ON THE DEVICE (square-and-multiply over the 32 host-computed g^(2^k)): no O(N) host loop, no
+// H2D copy and no stream synchronisation in the per-call paths (gl_fri_fold, gl_openings_lde)
 void fill_coset_table(gl_ctx* c, CosetTable& t, uint64_t g, uint32_t log_n) {
     t.g = g;
     if (log_n < 3) return;   // ntt_tiny_kernel takes g itself
-    std::vector<uint64_t> F((size_t)1 << log_n);
-    uint64_t cur = 1;
-    for (auto& x : F) { x = cur; cur = gl::h_mul(cur, g); }
-    t.F.ensure(F.size());
-    CUDA_CHECK(cudaMemcpyAsync(t.F.p, F.data(), F.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    ntt::PowTable pt{};
+    uint64_t sq = gl::canon(g);
+    for (uint32_t k = 0; k < 32; k++) { pt.g2k[k] = sq; sq = gl::h_mul(sq, sq); }
+    const uint64_t n = 1ULL << log_n;
+    t.F.ensure(n);
+    ntt::powers_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(t.F.p, n, pt);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// pre-scale table of a single coset NTT (the FRI layers re-evaluate on shift^arity; prove_openings on shift 7), kept per context:
+// a prover that proves repeatedly hits the cache; bounded at 2^25 words (256 MB)
+const CosetTable* get_coset_table(gl_ctx* c, uint64_t g, uint32_t log_len) {
+    auto key = std::make_pair(g, log_len);
+    auto it = c->coset_cache.find(key);
+    if (it != c->coset_cache.end()) return it->second.get();
+    const size_t words = (size_t)1 << log_len;
+    if (c->coset_cache_words + words > ((size_t)1 << 25)) {
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // a cached table may still be read by an enqueued pass
+        c->coset_cache.clear();
+        c->coset_cache_words = 0;
+    }
+    auto t = std::make_unique<CosetTable>();
+    fill_coset_table(c, *t, g, log_len);
+    c->coset_cache_words += words;
+    const CosetTable* p = t.get();
+    c->coset_cache[key] = std::move(t);
+    return p;
 }
 
 // coset s of the LDE evaluates at 7 * w_R^s * w_N^m
@@ -692,6 +717,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->roots.clear();
     c->pass_roots.clear();
     c->lde_tables.clear();
+    c->coset_cache.clear();
     c->in_stage.release(); c->vals.release(); c->scratch.release();
     DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -706,7 +732,15 @@ void gl_ctx_destroy(gl_ctx* c) {
     delete c;
 }
 
-const char* gl_ctx_last_error(gl_ctx* c) { return c ? c->err.c_str() : "null context"; }
+const char* gl_ctx_last_error(gl_ctx* c) {
+    // the message is copied under the context's mutex into a buffer owned by the CALLING thread: a second thread that shares the
+    // context and fails concurrently can no longer invalidate the pointer the first one is reading (valid until this thread's next call)
+    if (!c) return "null context";
+    static thread_local std::string tls_err;
+    std::lock_guard<std::mutex> lk(c->mu);
+    tls_err = c->err;
+    return tls_err.c_str();
+}
 uint64_t gl_ctx_stream(gl_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 
 int gl_commit(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
@@ -877,6 +911,39 @@ int gl_dev_ipc_free(gl_ctx* c, uint64_t* ptr) {
     GL_API_END(c)
 }
 
+int gl_dev_alloc(gl_ctx* c, uint64_t words, uint64_t** out_ptr) {
+    GL_API_BEGIN(c)
+    if (!out_ptr || words == 0) GL_THROW(GL_ERR_INVALID, "bad arguments");
+    uint64_t* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, words * 8));
+    *out_ptr = p;
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_free(gl_ctx* c, uint64_t* ptr) {
+    GL_API_BEGIN(c)
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (ptr) CUDA_CHECK(cudaFree(ptr));
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_upload(gl_ctx* c, const uint64_t* host_src, uint64_t* d_dst, uint64_t words) {
+    GL_API_BEGIN(c)
+    if ((!host_src || !d_dst) && words) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (words) CUDA_CHECK(cudaMemcpyAsync(d_dst, host_src, words * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+int gl_dev_download(gl_ctx* c, const uint64_t* d_src, uint64_t* host_dst, uint64_t words) {
+    GL_API_BEGIN(c)
+    if ((!host_dst || !d_src) && words) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (words) CUDA_CHECK(cudaMemcpyAsync(host_dst, d_src, words * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
 int gl_dev_repack(gl_ctx* c, const uint64_t* d_src, uint32_t src_pitch, uint32_t src_cols, uint64_t n_rows, uint64_t* d_dst,
                   uint32_t dst_pitch, uint32_t dst_col_off) {
     GL_API_BEGIN(c)
@@ -931,9 +998,16 @@ int gl_merkle_new(gl_ctx* c, const uint64_t* leaves, uint64_t n_leaves, uint32_t
     t->digests.ensure(n_dig * 4);
     t->d_cap.ensure(4ULL << cap_height);
     t->cap.resize(4ULL << cap_height);
-    if (leaf_len)
-        CUDA_CHECK(cudaMemcpy2DAsync(t->leaves.p, (size_t)pitch * 8, leaves, (size_t)leaf_len * 8, (size_t)leaf_len * 8, n_leaves,
-                                     cudaMemcpyHostToDevice, c->stream));
+    if (leaf_len) {
+        // packed host rows -> staging -> [n_leaves][pitch] with every word canonicalised (inputs may be any 64-bit representative;
+        // everything gl_tree_get / open_batch / read hands back is canonical, like every other ingest path)
+        const uint64_t total = n_leaves * leaf_len;
+        c->in_stage.ensure(total);
+        CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p, leaves, total * 8, cudaMemcpyHostToDevice, c->stream));
+        if (pitch != leaf_len) CUDA_CHECK(cudaMemsetAsync(t->leaves.p, 0, n_leaves * pitch * 8, c->stream));
+        ntt::repitch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(c->in_stage.p, leaf_len, t->leaves.p, pitch, 0, leaf_len, n_leaves);
+        CUDA_CHECK(cudaGetLastError());
+    }
     merkle_build(c, t->leaves.p, n_leaves, leaf_len, pitch, cap_height, t->digests.p, t->d_cap.p, nullptr, nullptr, nullptr);
     CUDA_CHECK(cudaMemcpyAsync(t->cap.data(), t->d_cap.p, 32ULL << cap_height, cudaMemcpyDeviceToHost, c->stream));
     if (out_digests && n_dig)
@@ -1162,8 +1236,9 @@ int gl_tree_get(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_row) 
 int gl_tree_get_lde_values(gl_ctx* c, gl_handle h, uint64_t index, uint64_t step, uint64_t* out_row) {
     GL_API_BEGIN(c)
     Tree* t = find_tree(c, h);
+    if (!out_row) GL_THROW(GL_ERR_INVALID, "out_row is NULL");
+    if (step != 0 && index > (t->n_leaves - 1) / step) GL_THROW(GL_ERR_INVALID, "index * step out of range");   // also rules out a wrapped product
     uint64_t i = index * step;
-    if (i >= t->n_leaves || !out_row) GL_THROW(GL_ERR_INVALID, "index * step out of range");
     uint64_t row = h_bitrev((uint32_t)i, log2_exact(t->n_leaves));
     CUDA_CHECK(cudaMemcpyAsync(out_row, t->leaves.p + row * t->pitch, (size_t)t->leaf_len * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1171,20 +1246,39 @@ int gl_tree_get_lde_values(gl_ctx* c, gl_handle h, uint64_t index, uint64_t step
     GL_API_END(c)
 }
 
+namespace {
+// MerkleTree::get + MerkleTree::prove for n indices: one gather kernel, at most two device->host copies
+void open_batch_impl(gl_ctx* c, Tree* t, const uint64_t* leaf_indices, uint32_t n, uint64_t* out_rows, uint64_t* out_siblings) {
+    if (n == 0) return;
+    if (!leaf_indices) GL_THROW(GL_ERR_INVALID, "leaf_indices is NULL");
+    for (uint32_t q = 0; q < n; q++)
+        if (leaf_indices[q] >= t->n_leaves) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
+    const uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
+    const size_t row_words = out_rows ? (size_t)n * t->leaf_len : 0, sib_words = out_siblings ? (size_t)n * log_sub * 4 : 0;
+    c->scratch.ensure(n + row_words + sib_words + 1);
+    uint64_t* d_idx = c->scratch.p;
+    uint64_t* d_rows = d_idx + n;
+    uint64_t* d_sib = d_rows + row_words;
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, leaf_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t total = (uint64_t)n * (t->leaf_len + 4 * log_sub);
+    if (total && (row_words || sib_words)) {
+        merkle::open_batch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(
+            t->leaves.p, t->pitch, t->leaf_len, t->digests.p, log_sub, d_idx, n, row_words ? d_rows : nullptr, sib_words ? d_sib : nullptr);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    if (row_words) CUDA_CHECK(cudaMemcpyAsync(out_rows, d_rows, 8 * row_words, cudaMemcpyDeviceToHost, c->stream));
+    if (sib_words) CUDA_CHECK(cudaMemcpyAsync(out_siblings, d_sib, 8 * sib_words, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+}  // namespace
+
 int gl_tree_prove(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_siblings) {
     GL_API_BEGIN(c)
     Tree* t = find_tree(c, h);
     if (leaf_index >= t->n_leaves) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
     uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
     if (!out_siblings && log_sub) GL_THROW(GL_ERR_INVALID, "out_siblings is NULL");   /* an empty proof needs no buffer */
-    uint64_t L = 1ULL << log_sub, sub = leaf_index >> log_sub, j = leaf_index & (L - 1);
-    const uint64_t* base = t->digests.p + 4 * (sub * 2 * (L - 1));
-    for (uint32_t layer = 0; layer < log_sub; layer++) {
-        CUDA_CHECK(cudaMemcpyAsync(out_siblings + 4 * layer, base + 4 * merkle::digest_index(layer, j ^ 1), 32,
-                                   cudaMemcpyDeviceToHost, c->stream));
-        j >>= 1;
-    }
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    open_batch_impl(c, t, &leaf_index, 1, nullptr, out_siblings);                      /* one gather + one copy, not one copy per level */
     return GL_OK;
     GL_API_END(c)
 }
@@ -1192,26 +1286,7 @@ int gl_tree_prove(gl_ctx* c, gl_handle h, uint64_t leaf_index, uint64_t* out_sib
 int gl_tree_open_batch(gl_ctx* c, gl_handle h, const uint64_t* leaf_indices, uint32_t n, uint64_t* out_rows, uint64_t* out_siblings) {
     GL_API_BEGIN(c)
     Tree* t = find_tree(c, h);
-    if (n == 0) return GL_OK;
-    if (!leaf_indices) GL_THROW(GL_ERR_INVALID, "leaf_indices is NULL");
-    for (uint32_t q = 0; q < n; q++)
-        if (leaf_indices[q] >= t->n_leaves) GL_THROW(GL_ERR_INVALID, "leaf index out of range");
-    const uint32_t log_sub = log2_exact(t->n_leaves) - t->cap_height;
-    const size_t row_words = (size_t)n * t->leaf_len, sib_words = (size_t)n * log_sub * 4;
-    c->scratch.ensure(n + row_words + sib_words + 1);
-    uint64_t* d_idx = c->scratch.p;
-    uint64_t* d_rows = d_idx + n;
-    uint64_t* d_sib = d_rows + row_words;
-    CUDA_CHECK(cudaMemcpyAsync(d_idx, leaf_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    const uint64_t total = (uint64_t)n * (t->leaf_len + 4 * log_sub);
-    if (total) {
-        merkle::open_batch_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, c->stream>>>(t->leaves.p, t->pitch, t->leaf_len, t->digests.p,
-                                                                                        log_sub, d_idx, n, d_rows, d_sib);
-        CUDA_CHECK(cudaGetLastError());
-    }
-    if (out_rows && row_words) CUDA_CHECK(cudaMemcpyAsync(out_rows, d_rows, 8 * row_words, cudaMemcpyDeviceToHost, c->stream));
-    if (out_siblings && sib_words) CUDA_CHECK(cudaMemcpyAsync(out_siblings, d_sib, 8 * sib_words, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    open_batch_impl(c, t, leaf_indices, n, out_rows, out_siblings);
     return GL_OK;
     GL_API_END(c)
 }
@@ -1343,9 +1418,7 @@ int gl_fri_fold(gl_ctx* c, gl_handle fh, const uint64_t beta[2]) {
     f->shift = gl::h_pow(f->shift, arity);
     // values <- coset_fft(coeffs, shift), kept in bit-reversed (in-place DIF) order
     uint32_t log_len = log2_exact(n_out);
-    CosetTable tab;
-    fill_coset_table(c, tab, f->shift, log_len);
-    run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, &tab, 2, nullptr);
+    run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, get_coset_table(c, f->shift, log_len), 2, nullptr);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return GL_OK;
     GL_API_END(c)
@@ -1479,10 +1552,7 @@ int gl_openings_lde(gl_ctx* c, gl_handle oh, uint32_t rate_bits, uint32_t cap_he
     if (log_len == 0) {
         CUDA_CHECK(cudaMemcpyAsync(f->values.p, f->coeffs.p, 16, cudaMemcpyDeviceToDevice, c->stream));
     } else {
-        CosetTable tab;
-        fill_coset_table(c, tab, gl::COSET_SHIFT, log_len);
-        run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, &tab, 2, nullptr);
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // tab is released at scope exit
+        run_ntt(c, f->coeffs.p, 2, f->values.p, 2, 2, log_len, false, get_coset_table(c, gl::COSET_SHIFT, log_len), 2, nullptr);
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     gl_handle h = c->next_handle++;

@@ -94,9 +94,10 @@ __global__ void open_batch_kernel(const uint64_t* __restrict__ leaves, uint32_t 
     const uint32_t q = (uint32_t)(i / per_q), w = (uint32_t)(i % per_q);
     const uint64_t leaf = indices[q];
     if (w < leaf_len) {
-        out_rows[(size_t)q * leaf_len + w] = leaves[leaf * pitch + w];
+        if (out_rows) out_rows[(size_t)q * leaf_len + w] = leaves[leaf * pitch + w];
         return;
     }
+    if (!out_siblings) return;
     const uint32_t layer = (w - leaf_len) >> 2, k = (w - leaf_len) & 3;
     const uint64_t L = 1ULL << log_sub, sub = leaf >> log_sub, j = (leaf & (L - 1)) >> layer;
     out_siblings[((size_t)q * log_sub + layer) * 4 + k] = digests[4 * (sub * 2 * (L - 1) + digest_index(layer, j ^ 1)) + k];

@@ -283,6 +283,18 @@ __global__ void scatter_copy16_kernel(const ulonglong2* __restrict__ src, uint32
     }
 }
 
+// out[j] = g^j (canonical), j < n <= 2^32, from the table g2k[k] = g^(2^k)
+struct PowTable { uint64_t g2k[32]; };
+__global__ void powers_kernel(uint64_t* __restrict__ out, uint64_t n, const PowTable pt) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t acc = 1;
+#pragma unroll 1
+    for (uint32_t k = 0, e = (uint32_t)j; e; k++, e >>= 1)
+        if (e & 1) acc = gl::mul(acc, pt.g2k[k]);
+    out[j] = gl::canon(acc);
+}
+
 // Column-major [n_cols][n_rows] (contiguous columns, as plonky2's Vec<PolynomialValues>) -> row-major
 // [n_rows][pitch], canonicalising on the way.  32x32 tiles through shared memory.
 __global__ void transpose_in_kernel(const uint64_t* __restrict__ src, uint64_t src_col_stride, uint64_t* __restrict__ dst,

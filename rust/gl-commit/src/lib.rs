@@ -65,8 +65,8 @@ pub struct Context {
     raw: *mut ffi::gl_ctx,
 }
 // the library takes the context's mutex on every call
+// Send only: one context per prover thread is the intended use (every call serialises on the context's mutex anyway).
 unsafe impl Send for Context {}
-unsafe impl Sync for Context {}
 
 impl Context {
     pub fn new(device: i32) -> Result<Self, Error> {
@@ -117,7 +117,8 @@ impl Context {
         if n == 0 || !n.is_power_of_two() {
             return Err(Error::Invalid("polynomial length must be a power of two".into()));
         }
-        if cap_height > 40 {
+        if cap_height > n.trailing_zeros() as usize + rate_bits {
+            // upstream's assert, checked before the cap is sized by 2^cap_height
             return Err(Error::Invalid(format!("cap_height={cap_height} should be at most log2(leaves.len())")));
         }
         let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
@@ -147,7 +148,9 @@ impl Context {
         if leaf_len == 0 || leaves.len() % leaf_len != 0 {
             return Err(Error::Invalid("leaves must be n_leaves * leaf_len words".into()));
         }
-        if cap_height > 40 {
+        let n_leaves = leaves.len() / leaf_len;
+        if cap_height >= 64 || n_leaves == 0 || (1usize << cap_height) > n_leaves {
+            // upstream's assert, checked before the cap is sized by 2^cap_height
             return Err(Error::Invalid(format!("cap_height={cap_height} should be at most log2(leaves.len())")));
         }
         let mut cap = vec![[0u64; 4]; 1 << cap_height];

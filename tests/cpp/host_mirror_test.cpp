@@ -307,7 +307,7 @@ static void test_fri_proof_host_arrays(Context& ctx) {
                 const size_t ab = cfg.arity[l], arity = size_t(1) << ab, leaf_index = x >> ab;
                 std::vector<F> leaf(o.leaves[l].begin() + leaf_index * 2 * arity, o.leaves[l].begin() + (leaf_index + 1) * 2 * arity);
                 std::vector<Ext> expect;
-                for (size_t k = 0; k < arity; k++) if (k != (x & (arity - 1))) expect.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});
+                for (size_t k = 0; k < arity; k++) expect.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});   // validate_shape: evals.len() == arity
                 ok &= rnd.steps[l].evals == expect;
                 MerkleCap cap;
                 cap.hashes.resize(size_t(1) << cfg.h);
@@ -427,7 +427,7 @@ static void test_prove_openings(Context& ctx, const Golden* golden) {
                 const size_t ab = cfg.arity[l], arity = size_t(1) << ab, leaf_index = x >> ab;
                 std::vector<F> leaf(o.leaves[l].begin() + leaf_index * 2 * arity, o.leaves[l].begin() + (leaf_index + 1) * 2 * arity);
                 std::vector<Ext> expect;
-                for (size_t k = 0; k < arity; k++) if (k != (x & (arity - 1))) expect.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});
+                for (size_t k = 0; k < arity; k++) expect.push_back(Ext{leaf[2 * k], leaf[2 * k + 1]});
                 ok &= rnd.steps[l].evals == expect && verify_path(leaf, leaf_index, rnd.steps[l].merkle_proof, proof.commit_phase_merkle_caps[l]);
                 x = leaf_index;
             }

@@ -339,7 +339,7 @@ def test_prove_openings_errors(ctx):
 def test_fri_query_rounds_open_and_verify(ctx, oc, cfg):
     """prove_openings -> fri_prover_query_rounds: every opened row equals the single-call readers (already checked against the
     oracle), every Merkle path verifies with the VERIFIER's rule against the committed cap, the commit-phase evaluations are the
-    layer leaves with the queried element removed (the structure oracle/gl_oracle.py · fri_prover_query_rounds restates)."""
+    whole layer leaves (`arity` elements; the structure oracle/gl_oracle.py · fri_prover_query_rounds restates)."""
     g = _g()
     log_n, widths, r, cap_h, arities, n_rounds = cfg
     n = 1 << log_n
@@ -363,11 +363,14 @@ def test_fri_query_rounds_open_and_verify(ctx, oc, cfg):
             assert oc.verify_path(row, x, sib, t.cap.hashes)
         for arity_bits, t, step in zip(arities, head.trees, rnd["steps"]):
             leaf = t.get(x >> arity_bits)
-            ev = leaf.reshape(-1, 2)
-            keep = [i for i in range(1 << arity_bits) if i != (x & ((1 << arity_bits) - 1))]
-            assert np.array_equal(step["evals"], ev[keep])
+            # as the verifier does (fri/verifier.rs · fri_verifier_query_round): evals has `arity` elements, the queried one is
+            # evals[x & (arity-1)], and the Merkle proof is checked over flatten(evals)
+            ev = np.asarray(step["evals"])
+            assert ev.shape == (1 << arity_bits, 2)
+            assert np.array_equal(ev[x & ((1 << arity_bits) - 1)], leaf.reshape(-1, 2)[x & ((1 << arity_bits) - 1)])
+            assert np.array_equal(ev.reshape(-1), leaf)
             assert np.array_equal(step["merkle_proof"], t.prove(x >> arity_bits))
-            assert oc.verify_path(leaf, x >> arity_bits, step["merkle_proof"], t.cap.hashes)
+            assert oc.verify_path(ev.reshape(-1), x >> arity_bits, step["merkle_proof"], t.cap.hashes)
             x >>= arity_bits
 
 

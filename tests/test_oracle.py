@@ -332,9 +332,10 @@ def test_fri_query_rounds_restatement_verifies():
         for arity_bits, tree, step in zip(arities, trees, rnd["steps"]):
             leaf = tree.get(x >> arity_bits)
             evals = list(step["evals"])
-            evals.insert(x & ((1 << arity_bits) - 1), (leaf[2 * (x & ((1 << arity_bits) - 1))], leaf[2 * (x & ((1 << arity_bits) - 1)) + 1]))
-            assert [w for e in evals for w in e] == list(leaf)
-            assert o.verify_merkle_proof_to_cap(leaf, x >> arity_bits, tree.cap, step["merkle_proof"])
+            assert len(evals) == 1 << arity_bits                       # validate_shape: evals.len() == arity
+            flat = [w for e in evals for w in e]
+            assert flat == list(leaf)
+            assert o.verify_merkle_proof_to_cap(flat, x >> arity_bits, tree.cap, step["merkle_proof"])
             x >>= arity_bits
 
 
