@@ -25,6 +25,7 @@
 #include "merkle.cuh"
 #include "microbench.cuh"
 #include "ntt.cuh"
+#include "ntt2.cuh"
 #include "openings.cuh"
 
 namespace {
@@ -188,6 +189,8 @@ struct gl_ctx {
     //       ship them (one strided 2-D peer copy per owner segment) while the next coset's NTT runs — no SM time, no NVLink
     //       stalls inside the NTT
     int scatter_mode = 3;
+    int ntt_version = 2;                  // GL_NTT_VERSION=1 selects the first-generation pass kernel (ntt.cuh) for A/B measurements
+    int ntt_g10 = 8;                      // GL_NTT_G10=4: 4-column tiles for the 10-stage passes (smaller CTAs)
     cudaStream_t send_stream = nullptr;
     cudaEvent_t ev_ntt[2] = {}, ev_sent[2] = {};
     bool sent_pending[2] = {false, false};
@@ -224,7 +227,7 @@ const uint64_t* get_roots(gl_ctx* c, uint32_t log_n) {
 const uint64_t* get_pass_roots(gl_ctx* c, uint32_t a) {
     auto it = c->pass_roots.find(a);
     if (it != c->pass_roots.end()) return it->second->p;
-    const size_t T = (size_t)1 << a, n = T - (T >> 3);
+    const size_t T = (size_t)1 << a, n = T;   // the full circle: radix-16 rounds reach exponents up to 15T/16
     std::vector<uint64_t> w(n ? n : 1);
     uint64_t root = gl::h_root_of_unity(a), cur = 1;
     for (size_t e = 0; e < n; e++) {
@@ -293,6 +296,41 @@ const std::vector<CosetTable>& get_lde_tables(gl_ctx* c, uint32_t log_n, uint32_
 template <int G, int A>
 void launch_pass_a(gl_ctx* c, const ntt::PassParams& p, uint32_t threads, size_t smem, uint32_t grid) {   // smem <= 44 KB for every (G, a)
     ntt::ntt_pass_kernel<G, A><<<grid, threads, smem, c->stream>>>(p);
+}
+// second-generation pass (ntt2.cuh): two columns per thread, carry-save butterflies, all-shift radix-16 last round
+template <int G, int A>
+void launch_pass2_a(gl_ctx* c, const ntt::PassParams& p, uint32_t grid) {
+    constexpr size_t smem = ntt2::smem_words<A, G>() * 8;
+    constexpr uint32_t threads = (1u << A) * G / 16;
+    if (smem > 48 * 1024) {
+        static std::once_flag once[8];   // per device: the attribute belongs to the function on a device
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        cudaError_t e = cudaSuccess;
+        std::call_once(once[dev & 7], [&] { e = cudaFuncSetAttribute(ntt2::ntt_pass_kernel<G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        CUDA_CHECK(e);
+    }
+    ntt2::ntt_pass_kernel<G, A><<<grid, threads, smem, c->stream>>>(p);
+}
+template <int G>
+bool launch_pass2(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* launches) {
+    p.ncg = cols_padded / G;
+    const uint64_t grid = (uint64_t)p.ncg << (p.log_n - p.a);
+    if (grid >= (1ULL << 31)) GL_THROW(GL_ERR_UNSUPPORTED, "NTT grid too large");
+    switch (p.a) {
+        case 3: launch_pass2_a<G, 3>(c, p, (uint32_t)grid); break;
+        case 4: launch_pass2_a<G, 4>(c, p, (uint32_t)grid); break;
+        case 5: launch_pass2_a<G, 5>(c, p, (uint32_t)grid); break;
+        case 6: launch_pass2_a<G, 6>(c, p, (uint32_t)grid); break;
+        case 7: launch_pass2_a<G, 7>(c, p, (uint32_t)grid); break;
+        case 8: launch_pass2_a<G, 8>(c, p, (uint32_t)grid); break;
+        case 9: launch_pass2_a<G, 9>(c, p, (uint32_t)grid); break;
+        case 10: launch_pass2_a<G, 10>(c, p, (uint32_t)grid); break;
+        default: return false;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (launches) (*launches)++;
+    return true;
 }
 
 template <int G>
@@ -369,6 +407,16 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
             p.dst = dst; p.dst_pitch = dst_pitch;
         }
         int g = G;
+        if (c->ntt_version >= 2 && (g == 8 || g == 4)) {
+            // 128-bit accesses need even pitches and 16-byte aligned bases (true for every buffer this library lays out)
+            const bool aligned = p.src_pitch % 2 == 0 && p.dst_pitch % 2 == 0 && ((uintptr_t)p.src % 16 == 0) && ((uintptr_t)p.dst % 16 == 0);
+            if (g == 8 && p.a == 10 && c->ntt_g10 == 4) g = 4;
+            if (aligned && (g == 8 ? launch_pass2<8>(c, p, cols_padded, launches) : launch_pass2<4>(c, p, cols_padded, launches))) {
+                log_blk -= passes[i];
+                continue;
+            }
+            g = G;
+        }
         if (g == 8 && p.a == 10) g = 4;   // keep 512 threads / 40 KB shared memory per CTA
         switch (g) {
             case 8: launch_pass<8>(c, p, cols_padded, launches); break;
@@ -698,6 +746,8 @@ int gl_ctx_create(gl_ctx** out, int device) {
             cudaEventCreateWithFlags(&c->ev_sent[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (const char* m = getenv("GL_SCATTER_MODE")) c->scatter_mode = atoi(m);
     if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
+    if (const char* m = getenv("GL_NTT_VERSION")) c->ntt_version = atoi(m);
+    if (const char* m = getenv("GL_NTT_G10")) c->ntt_g10 = atoi(m);
     if (cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_copyback, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     for (auto& e : c->ev)
