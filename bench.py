@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU column->row exchange (DESIGN.md §6)")
+    ap.add_argument("--workload", default="commit", choices=["commit", "wrapper"],
+                    help="commit: the headline PolynomialBatch commit; wrapper: the wrapper-circuit-shaped prove pipeline (commits 86/135/20/16 "
+                         "x 2^16 -> prove_openings -> FRI [4,4,4] -> PoW 16 -> 28 query rounds), second line of BASELINE.json's metric")
+    ap.add_argument("--single-process", action="store_true",
+                    help="--gpus N from ONE process through gl_commit_multi (the form CircuitData::prove can call), instead of torchrun")
     return ap.parse_args()
 
 
@@ -208,10 +213,155 @@ def synth_columns(torch, dev, cols, n, seed):
     return z.view(cols, n)
 
 
+def run_wrapper(a):
+    """--workload wrapper: the hot-path part of `data.prove(pw)` (/root/reference/src/p3/mod.rs:258-262) at the wrapper circuit's
+    shape, end to end through the reference-facing interface with HOST (pinned) columns, and the CPU oracle on the same transcript
+    beside it; every proof field is hashed and compared.  One JSON line, metric `wrap_hot_path_ms` (lower is better)."""
+    import numpy as np
+    import wrapper_pipeline as wp
+    log_n = 16 if a.log_n == 20 else a.log_n
+    cols = wp.make_columns(log_n)
+    line = {"metric": "wrap_hot_path_ms (wrapper-shaped commits 86/135/20/16 x 2^%d, r=3, h=4 -> prove_openings -> FRI [4,4,4] -> PoW 16 -> "
+                      "28 query rounds)" % log_n, "unit": "ms", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
+            "config": {"workload": "wrapper-circuit-shaped prove pipeline (tests/wrapper_pipeline.py): the commitment hot path of data.prove at "
+                                   "src/p3/mod.rs:258-262; column contents synthetic, shapes/call order/proof bytes the reference's",
+                       "log_n": log_n, "widths": list(wp.WIDTHS), "rate_bits": 3, "cap_height": 4, "arities": list(wp.ARITIES),
+                       "pow_bits": wp.POW_BITS, "query_rounds": wp.N_QUERIES,
+                       "note": "fib(64) wrap-prove ms itself is not runnable here (no Rust toolchain); this is BASELINE.md §4.6's surrogate"}}
+    if a.impl == "reference":
+        from oracle_c import OracleC
+        oc = OracleC()
+        oc.set_threads(host_threads())
+        tm = {}
+        for _ in range(min(a.warmup, 1)):
+            wp.run_oracle(oc, cols, log_n)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            proof = wp.run_oracle(oc, cols, log_n, timings=tm)
+        ms = (time.perf_counter() - t0) / a.steps * 1e3
+        line.update({"impl": "reference", "value": round(ms, 2), "ms_per_step": round(ms, 2), "stage_ms": {k: round(v, 2) for k, v in tm.items()},
+                     "cpu_baseline": {"value": round(ms, 2), "unit": "ms", "cores": oc.num_threads(), "kind": "port",
+                                      "sample": "the whole pipeline, oracle/gl_oracle.c + Python glue"},
+                     "e2e": {"value": round(ms, 2), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                     "parity": {"proof_sha256": wp.digest(proof)}})
+        print(json.dumps(line), flush=True)
+        return
+    import plonky25_b200 as g
+    ctx = g.Context(0)
+    lib = ctx.lib
+    # pinned host columns (what a binding that cares about PCIe hands over; gl_host_alloc)
+    pinned = []
+    for c in cols:
+        ptr = lib.gl_host_alloc(c.nbytes)
+        arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=c.shape)
+        arr[:] = c
+        pinned.append(arr)
+    sampler = ClockSampler(0)
+    for _ in range(max(a.warmup, 0)):
+        wp.run_product(g, ctx, pinned, log_n)
+    sampler.start()
+    time.sleep(0.2)
+    acc = {}
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        tm = {}
+        proof = wp.run_product(g, ctx, pinned, log_n, timings=tm)
+        for k, v in tm.items():
+            acc[k] = acc.get(k, 0.0) + v
+    t1 = time.perf_counter()
+    ms = (t1 - t0) / a.steps * 1e3
+    clocks = sampler.stop(t0, t1)
+    h2d = sum(c.nbytes for c in cols)
+    d2h = sum(np.asarray(x).nbytes for rnd in proof["query_rounds"] for pair in rnd["initial"] + rnd["steps"] for x in pair) + \
+        sum(np.asarray(c).nbytes for c in proof["commit_caps"] + proof["commit_phase_caps"]) + np.asarray(proof["final_poly"]).nbytes
+    parity = {"proof_sha256": wp.digest(proof), "oracle": None, "match": None}
+    cpu = None
+    if not a.no_cpu_baseline:
+        from oracle_c import OracleC
+        oc = OracleC()
+        oc.set_threads(host_threads())
+        tmc = {}
+        ref = wp.run_oracle(oc, cols, log_n, timings=tmc)
+        parity.update({"oracle": "oracle/gl_oracle.c on the same columns and transcript", "match": wp.digest(ref) == parity["proof_sha256"]})
+        cpu = {"value": round(tmc["total"], 2), "unit": "ms", "cores": oc.num_threads(), "kind": "port",
+               "sample": "the whole pipeline once", "stage_ms": {k: round(v, 2) for k, v in tmc.items()}}
+    line.update({"value": round(ms, 3), "ms_per_step": round(ms, 3), "stage_ms": {k: round(v / a.steps, 3) for k, v in acc.items()},
+                 "clocks": clocks, "gpu_launches": None,
+                 "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                         "api": "PolynomialBatch.from_values/from_coeffs -> prove_openings -> fri_prover_query_rounds (plonky2.5_b200/api.py over "
+                                "include/gl_commit.h), pinned host columns in, proof fields out"},
+                 "cpu_baseline": cpu, "parity": parity})
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if parity["match"] is False:
+        raise SystemExit("PARITY MISMATCH: the wrapper-pipeline proof differs from the oracle's")
+
+
+def run_single_process(a):
+    """--gpus N --single-process: ONE process drives N GPUs through gl_commit_multi (one context per device, worker threads inside the
+    library) — the form CircuitData::prove (/root/reference/src/p3/mod.rs:260), a single process, can actually call.  Host (pinned)
+    columns in, cap out: the number is end-to-end by construction, so `value` and `e2e.value` are the same measurement."""
+    import numpy as np
+    import plonky25_b200 as g
+    import headline
+    from oracle_c import splitmix_columns
+    log_n, cols, r, h = a.log_n, a.cols, a.rate_bits, a.cap_height
+    n = 1 << log_n
+    ctxs = [g.Context(d) for d in range(a.gpus)]
+    lib = ctxs[0].lib
+    ptr = lib.gl_host_alloc(cols * n * 8)
+    harr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(cols, n))
+    harr[:] = splitmix_columns(1, cols, n)
+    sampler = ClockSampler(0)
+
+    def step():
+        cap, trees = g.commit_multi(ctxs, list(harr), r, h)
+        for t in trees:
+            t.free()
+        return cap.hashes
+
+    for _ in range(max(a.warmup, 0)):
+        step()
+    sampler.start()
+    time.sleep(0.2)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cap = step()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    ms = (t1 - t0) / a.steps * 1e3
+    val = cols * n / (ms * 1e-3) / 1e6
+    stage = {}
+    for d, c in enumerate(ctxs):
+        st, _ = c.stage_times()
+        stage[f"gpu{d}"] = {k: round(v, 3) for k, v in st.items() if v}
+    parity = headline.parity_block(cap, log_n, cols, r, h, seed=1)
+    line = {"metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "mode": "single process, gl_commit_multi: one context per device, column shards -> "
+                                                             "copy-engine peer shipments -> per-device subtrees -> cap concatenated on the host",
+                       "timing": "host wall clock around the synchronous call (the call returns after every device's cap slice is on the host)"},
+            "stage_ms_last_call": stage, "clocks": clocks, "gpu_launches": None,
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": cols * n * 8, "d2h_bytes_per_step": 32 << h,
+                    "ms_per_step": round(ms, 4), "api": "gl_commit_multi (include/gl_commit.h) with pinned host columns"},
+            "roofline": None, "cpu_baseline": None, "parity": parity}
+    print(json.dumps(line), flush=True)
+    for c in ctxs:
+        c.close()
+    if parity["match"] is False:
+        raise SystemExit("PARITY MISMATCH: the Merkle cap differs from the oracle's golden (see the `parity` object)")
+
+
 def main():
     a = parse()
+    if a.workload == "wrapper":
+        return run_wrapper(a)
     if a.impl == "reference":
         return run_reference(a)
+    if a.single_process and a.gpus > 1:
+        return run_single_process(a)
 
     import numpy as np
     import torch

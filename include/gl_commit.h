@@ -45,6 +45,9 @@ enum {
 int gl_abi_version(void);
 const char* gl_strerror(int code);
 
+/* number of CUDA devices visible to the process (0 without a driver/device) */
+int gl_device_count(void);
+
 /* ---- context --------------------------------------------------------------------------------------------- */
 int gl_ctx_create(gl_ctx** out, int device);
 void gl_ctx_destroy(gl_ctx* ctx);
@@ -77,9 +80,8 @@ int gl_commit(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_
  * and gl_tree_prove on it returns exactly MerkleTree::prove(i) (the subtree roots are cap entries, so no path crosses contexts).
  * The shard trees carry no coefficient matrix (gl_tree_read(GL_PART_COEFFS) is refused) and gl_tree_get_lde_values does not
  * apply to them.  All contexts are locked for the duration of the call; status and message are reported through ctxs[0].
- * ROUND-1 STATUS: bit-exact on a B200 with 2, 4 and 8 contexts sharing ONE device (cap, every shard's leaves and digests, paths ==
- * oracle; tests/test_gpu_parity.py); with one device per context the only additional step is cudaDeviceEnablePeerAccess, not yet run
- * on hardware (GL_TEST_COMMIT_MULTI_DEVICES=N spreads the test's contexts over N GPUs).                                          */
+ * Tested bit-exact against the oracle with several contexts on one device and with one device per context (tests/test_gpu_parity.py
+ * spreads the contexts over every visible GPU; bench.py --gpus N --single-process times it).                                      */
 int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
                     uint32_t cap_height, int input_is_coeffs, uint64_t* out_cap, gl_handle* out_trees);
 

@@ -27,6 +27,7 @@ u64p = POINTER(c_uint64)
 SIGNATURES = {
     "gl_abi_version": (c_int, []),
     "gl_strerror": (c_char_p, [c_int]),
+    "gl_device_count": (c_int, []),
     "gl_ctx_create": (c_int, [POINTER(c_void_p), c_int]),
     "gl_ctx_destroy": (None, [c_void_p]),
     "gl_ctx_last_error": (c_char_p, [c_void_p]),

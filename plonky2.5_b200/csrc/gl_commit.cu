@@ -712,6 +712,12 @@ extern "C" {
 
 int gl_abi_version(void) { return GL_ABI_VERSION; }
 
+int gl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 const char* gl_strerror(int code) {
     switch (code) {
         case GL_OK: return "ok";

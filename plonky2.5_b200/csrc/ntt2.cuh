@@ -206,7 +206,8 @@ __device__ __forceinline__ uint64_t* dest(const ntt::PassParams& p, uint32_t pro
 
 // G columns per tile (4 or 8), 2^A rows; (2^A * G) / 16 threads, 16 elements each
 template <int G, int A>
-__global__ void __launch_bounds__((1 << A) * G / 16 >= 32 ? (1 << A) * G / 16 : 32)
+__global__ void __launch_bounds__((1 << A) * G / 16 >= 32 ? (1 << A) * G / 16 : 32,
+                                   (1 << A) * G / 16 >= 32 ? 1024 / ((1 << A) * G / 16) : 32)   // 1024 threads per SM => <= 64 registers
 ntt_pass_kernel(const ntt::PassParams p) {
     constexpr int NR = plan_n(A);
     constexpr uint32_t T = 1u << A, G2 = G / 2, PAD = pad_shift<A>();
@@ -214,7 +215,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
     uint64_t* tile = sm2;                                     // [T + T/2^PAD][G]
     uint64_t* Wl = sm2 + (size_t)(T + (T >> PAD)) * G;        // w_T^j, j < T
     const uint32_t tid = threadIdx.x;
-    constexpr uint32_t NT = T * G / 16;
+    // launched with exactly T * G / 16 threads: every thread owns 16 elements of the tile
     const uint32_t cg = blockIdx.x % p.ncg, tile_id = blockIdx.x / p.ncg;
     const uint32_t b_lo = p.log_blk - A;
     const uint32_t o_lo = tile_id & ((1u << b_lo) - 1), o_hi = tile_id >> b_lo;
@@ -228,7 +229,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
     uint64_t u[16];      // radix-16 view: u[e] = column col1 of tile row insk(q16, sh, e, 4)
     constexpr int K0 = plan_k(A, 0);
     constexpr uint32_t SH0 = A - K0;
-    if (tid < NT) {
+    {
         if (K0 == 3) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
@@ -245,7 +246,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
     }
     if (NR > 1)
         for (uint32_t e = tid; e < T; e += blockDim.x) Wl[e] = __ldg(p.Wa + e);
-    if (p.pre != nullptr && tid < NT) {
+    if (p.pre != nullptr) {
         if (K0 == 3) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
@@ -274,7 +275,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
             // exchange: the previous round's elements go to the tile, this round's come back
             const int kp = plan_k(A, r - 1);
             const uint32_t shp = A - done;
-            if (tid < NT) {
+            {
                 if (kp == 3) {
 #pragma unroll
                     for (int e = 0; e < 8; e++)
@@ -285,7 +286,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
                 }
             }
             __syncthreads();
-            if (tid < NT) {
+            {
                 if (k == 4) {
 #pragma unroll
                     for (int e = 0; e < 16; e++) u[e] = tile[(size_t)phys(insk(q16, sh, e, 4)) * G + c1];
@@ -297,7 +298,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
             }
             if (!last) __syncthreads();            // the tile is rewritten by the next exchange
         }
-        if (tid < NT) {
+        {
             if (k == 4) {
                 dft16_cs(u);
                 if (!last) {
@@ -334,10 +335,30 @@ ntt_pass_kernel(const ntt::PassParams p) {
         }
         done += k;
     }
-    if (tid >= NT) return;
     // ---- the finished tile leaves: inter-pass twiddle / 1/N / canonical form, then the store of this pass's mode
     constexpr int KL = plan_k(A, NR - 1);
     if (KL == 4) {
+        // the two shapes every LDE coset runs (16 of the 18 launches of a commit) without per-element mode branches: plain row-major
+        // stores, no 1/N; the 16 rows of a thread are 2^b_lo rows apart, so one pointer walks them
+        if (p.store_mode == 0 && p.scale == 1) {
+            uint64_t* d = p.dst + (uint64_t)(row_base | ((q16 << 4) << b_lo)) * p.dst_pitch + col1;
+            const uint64_t stride = (uint64_t)p.dst_pitch << b_lo;
+            if (b_lo == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) d[e * stride] = gl::canon(u[e]);
+            } else {
+                // inter-pass twiddle w_{2^log_blk}^(o_lo * bitrev_A(l)), l = 16 q16 + e: bitrev_A(l) = bitrev_4(e) * 2^(A-4) + bitrev_(A-4)(q16)
+                const uint32_t N = 1u << p.log_n, sh = p.log_n - p.log_blk;
+                const uint32_t ex0 = (o_lo * gl::bitrev32(q16, A - 4)) << sh, exs = (o_lo << (A - 4)) << sh;
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const uint32_t ex = ex0 + exs * brev_const(e, 4);
+                    const uint64_t w = ex >= (N >> 1) ? gl::P - __ldg(p.W + (ex - (N >> 1))) : __ldg(p.W + ex);
+                    d[e * stride] = gl::mul(u[e], w);
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const uint32_t l = insk(q16, 0, e, 4);

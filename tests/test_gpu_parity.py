@@ -416,7 +416,8 @@ def test_commit_multi_single_process(oc, cfg):
     with one device per context): cap, every shard's leaves and digests, rows and paths equal the single commit of the oracle."""
     g = _g()
     world, log_n, n_cols, r, cap_h = cfg
-    n_dev = int(os.environ.get("GL_TEST_COMMIT_MULTI_DEVICES", "1"))     # > 1: spread the contexts over that many GPUs
+    # one device per context when the box has them (peer access over NVLink), else the contexts share devices
+    n_dev = int(os.environ.get("GL_TEST_COMMIT_MULTI_DEVICES", "0")) or max(1, min(world, g._lib.load().gl_device_count()))
     ctxs = [g.Context(k % n_dev) for k in range(world)]
     try:
         cols = splitmix_columns(700 + world + log_n, n_cols, 1 << log_n)

@@ -137,7 +137,8 @@ def build_cpp_tools() -> dict:
     from oracle_c import build_oracle
     lib, ora = g.build(), build_oracle()
     os.makedirs(OUT_DIR, exist_ok=True)
-    out = {"cbench": os.path.join(OUT_DIR, "cbench"), "variant_bench": os.path.join(OUT_DIR, "variant_bench")}
+    out = {"cbench": os.path.join(OUT_DIR, "cbench"), "variant_bench": os.path.join(OUT_DIR, "variant_bench"),
+           "devbench": os.path.join(OUT_DIR, "devbench")}
     hdr = os.path.join(ROOT, "include", "gl_commit.h")
 
     def stale(exe, deps):
@@ -146,6 +147,9 @@ def build_cpp_tools() -> dict:
     src = os.path.join(ROOT, "tools", "cbench.cpp")
     if stale(out["cbench"], [src, hdr, lib]):
         _cxx([src, "-o", out["cbench"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
+    src = os.path.join(ROOT, "tools", "devbench.cpp")
+    if stale(out["devbench"], [src, hdr, lib]):
+        _cxx([src, "-o", out["devbench"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
     src = os.path.join(ROOT, "tests", "cpp", "variant_bench.cpp")
     if stale(out["variant_bench"], [src, hdr, ora]):
         _cxx([src, "-o", out["variant_bench"], "-L", os.path.dirname(ora), "-lgl_oracle", "-Wl,-rpath,$ORIGIN/../../../oracle", "-ldl", "-pthread"])
