@@ -286,8 +286,49 @@ def run_wrapper(a):
         parity.update({"oracle": "oracle/gl_oracle.c on the same columns and transcript", "match": wp.digest(ref) == parity["proof_sha256"]})
         cpu = {"value": round(tmc["total"], 2), "unit": "ms", "cores": oc.num_threads(), "kind": "port",
                "sample": "the whole pipeline once", "stage_ms": {k: round(v, 2) for k, v in tmc.items()}}
+    # ---- gate-constraint evaluation over the resident LDE rows of a wires commit at the wrapper's R = 2^19
+    gate_eval = None
+    try:
+        import random
+        import gates_oracle as go
+        wires = g.PolynomialBatch.from_values(list(pinned[1]), 3, False, 4, ctx=ctx)
+        R = 1 << (log_n + 3)
+        alphas = np.array([0x1234567890ABCDEF % P, 0xFEDCBA9876543210 % P], dtype=np.uint64)
+        q, ms_ = ctypes.c_uint64(), ctypes.c_float()
+        assert lib.gl_quotient_begin(ctx.handle, wires.merkle_tree._h, 2, ctypes.byref(q)) == 0
+        t_g = {}
+        for name, kind, param, off in (("Poseidon2Gate", 0, 0, 0), ("U32ArithmeticGate", 1, 3, 123)):
+            best = 1e9
+            for _ in range(3):
+                assert lib.gl_quotient_add_gate(ctx.handle, q.value, kind, param, alphas.ctypes.data, off, 0, 0) == 0
+                lib.gl_ctx_aux_ms(ctx.handle, ctypes.byref(ms_))
+                best = min(best, ms_.value)
+            t_g[name] = best
+        # parity on sampled rows: (3 accumulations of each gate) == 3 * reduce_with_powers of the oracle's constraints of that leaf row
+        out = np.zeros((2, R), dtype=np.uint64)
+        assert lib.gl_quotient_read(ctx.handle, q.value, out.ctypes.data) == 0
+        lib.gl_quotient_end(ctx.handle, q.value)
+        rnd = random.Random(1)
+        rows = [0, R - 1] + [rnd.randrange(R) for _ in range(14)]
+        lw = wires.merkle_tree.open_batch(rows)[0]
+        ok = True
+        for j, row in enumerate(rows):
+            c0, c1 = go.poseidon2_gate_eval(lw[j].tolist()), go.u32_arithmetic_eval(lw[j].tolist()[:114], num_ops=3)
+            for k in range(2):
+                want = 3 * (go.reduce_with_powers(c0, int(alphas[k])) + go.reduce_with_powers(c1, int(alphas[k]), start_power=123)) % P
+                ok = ok and int(out[k, row]) == want
+        wires.merkle_tree.free()
+        gate_eval = {"rows": R, "n_challenges": 2, "ms": {k: round(v, 4) for k, v in t_g.items()},
+                     "melem_per_s": {k: round(R * 135 / (v * 1e-3) / 1e6, 1) for k, v in t_g.items()},
+                     "mconstraints_per_s": {"Poseidon2Gate": round(R * 123 / (t_g["Poseidon2Gate"] * 1e-3) / 1e6, 1),
+                                            "U32ArithmeticGate": round(R * 108 / (t_g["U32ArithmeticGate"] * 1e-3) / 1e6, 1)},
+                     "unit": "wire elements of the LDE rows consumed per second (R x 135 / kernel time, CUDA events)",
+                     "parity": {"sampled_rows": len(rows), "match": bool(ok),
+                                "oracle": "oracle/gates_oracle.py (restates poseidon2_gate.rs:233-310, arithmetic_u32.rs:103-166)"}}
+    except Exception as e:   # a reported extra: never lose the main line over it
+        gate_eval = {"error": repr(e)}
     line.update({"value": round(ms, 3), "ms_per_step": round(ms, 3), "stage_ms": {k: round(v / a.steps, 3) for k, v in acc.items()},
-                 "clocks": clocks, "gpu_launches": None,
+                 "clocks": clocks, "gpu_launches": None, "gate_eval": gate_eval,
                  "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                          "api": "PolynomialBatch.from_values/from_coeffs -> prove_openings -> fri_prover_query_rounds (plonky2.5_b200/api.py over "
                                 "include/gl_commit.h), pinned host columns in, proof fields out"},

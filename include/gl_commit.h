@@ -151,6 +151,33 @@ int gl_openings_end(gl_ctx* ctx, gl_handle openings);
 /* read the current coefficients (len extension elements) / bit-reversed values of a gl_fri state (tests, debugging) */
 int gl_fri_read(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* out_values_bitrev_ext, uint64_t* out_len);
 
+/* ---- gate constraints over the resident LDE rows, and witness rows -------------------------------------
+ * plonky2 plonk/prover.rs · compute_quotient_polys evaluates every gate's constraints at every point of the LDE coset and combines them
+ * with powers of the challenges alpha_k (plonk/vanishing_poly.rs · evaluate_gate_constraints_base_batch + plonk_common.rs ·
+ * reduce_with_powers).  The rows are already in HBM: a leaf row of the wires commit IS the wire vector at LDE point bitrev(row).
+ * Gates implemented are the reference's own, whose source is in its tree:
+ *   GL_GATE_POSEIDON2       /root/reference/src/common/poseidon2/poseidon2_gate.rs:233-310   135 wires, 123 constraints (param unused)
+ *   GL_GATE_U32_ARITHMETIC  /root/reference/src/common/u32/gates/arithmetic_u32.rs:103-166    param = num_ops (3 at 135 wires / 80 routed):
+ *                                                                                             38*num_ops wires, 36*num_ops constraints
+ * gl_quotient_add_gate:  acc[k][row] += filter(row) * sum_i alphas[k]^(constraint_offset + i) * constraint_i(wires(row)),  k < n_challenges
+ * (alphas are BASE-field challenges, as upstream; filter(row) = column filter_col of the batch filter_batch at the same row — the LDE of the
+ * gate's selector filter — or 1 when filter_batch == 0).  gl_quotient_read: [n_challenges][R] words, row order = the leaves' (bit-reversed). */
+enum { GL_GATE_POSEIDON2 = 0, GL_GATE_U32_ARITHMETIC = 1 };
+int gl_gate_num_wires(int kind, uint32_t param);
+int gl_gate_num_constraints(int kind, uint32_t param);
+/* every constraint value of every row, uncombined (host rows [n_rows][num_wires] -> out [n_rows][num_constraints]); tests, debugging */
+int gl_gate_eval_rows(gl_ctx* ctx, int kind, uint32_t param, const uint64_t* rows, uint64_t n_rows, uint64_t* out);
+int gl_quotient_begin(gl_ctx* ctx, gl_handle wires_batch, uint32_t n_challenges, gl_handle* out_quotient);
+int gl_quotient_add_gate(gl_ctx* ctx, gl_handle quotient, int kind, uint32_t param, const uint64_t* alphas, uint32_t constraint_offset,
+                         gl_handle filter_batch, uint32_t filter_col);
+int gl_quotient_read(gl_ctx* ctx, gl_handle quotient, uint64_t* out);
+int gl_quotient_end(gl_ctx* ctx, gl_handle quotient);
+/* CUDA-event milliseconds of the last gl_quotient_add_gate / gl_poseidon2_gate_witness kernel on this context */
+int gl_ctx_aux_ms(gl_ctx* ctx, float* out_ms);
+/* witness generation for Poseidon2Gate rows (poseidon2_gate.rs:447-523 · Poseidon2Generator::run_once): inputs [n][13] = the 12 state
+ * inputs + the swap flag of each row -> out_rows [n][135], every wire of the row (deltas, S-box inputs of all rounds, outputs)        */
+int gl_poseidon2_gate_witness(gl_ctx* ctx, const uint64_t* inputs, uint64_t n, uint64_t* out_rows);
+
 /* ---- FRI proof of work: fri_proof_of_work  (plonky2 fri/prover.rs) ---------------------------------------------
  * sponge_state / input_buffer: the caller's Challenger fields (sponge_state, pending input_buffer, n_inputs < 8).
  * Finds the SMALLEST canonical w such that, with the pending inputs written into the state and w in the next input

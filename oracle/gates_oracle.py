@@ -1,0 +1,239 @@
+"""CPU oracle for the gate layer of SURVEY.md §8(f) ranks 3-4 — TEST INFRASTRUCTURE ONLY (imported by tests/ and bench.py's
+baseline legs; the product never touches oracle/).
+
+Unlike the commitment path, the source of these functions IS in the reference tree, so this is a line-by-line restatement of
+Rust that can be read next to it ("parity pinned by the reference source"):
+
+  poseidon2()                      /root/reference/src/common/poseidon2/poseidon2.rs:59-91      Poseidon2::poseidon2
+  matmul_external / matmul_m4      poseidon2.rs:127-146, 185-245
+  matmul_internal                  poseidon2.rs:164-182
+  Poseidon2Gate wire layout        /root/reference/src/common/poseidon2/poseidon2_gate.rs:82-142
+  poseidon2_gate_eval()            poseidon2_gate.rs:233-310   eval_unfiltered_base_one (123 constraints, degree 7)
+  poseidon2_gate_witness()         poseidon2_gate.rs:447-523   Poseidon2Generator::run_once
+  u32_arithmetic_eval()            /root/reference/src/common/u32/gates/arithmetic_u32.rs:103-166 (eval_unfiltered; the packed base
+                                   evaluator :285-340 computes the same values), num_ops = 3 for the 135-wire / 80-routed config (:52-55)
+  u32_arithmetic_witness()         arithmetic_u32.rs · U32ArithmeticGenerator::run_once (output split into halves, 2-bit limbs, inverse)
+  reduce_with_powers()             plonky2 plonk/plonk_common.rs · reduce_with_powers (sum_i alpha^i * c_i), restated
+
+Constants come from oracle/poseidon2_constants.py, generated from the reference source by tools/gen_poseidon2_constants.py.
+The reference holds no Poseidon2 known-answer vector (the block at poseidon2_goldilocks.rs:190-211 is plonky2's *Poseidon*, SURVEY F6,
+and its checker is tautological); these constants are not the HorizenLabs instance either, so no published vector applies.  What pins
+the restatement is the source itself plus the gate's own consistency: a row filled by the generator satisfies all 123 constraints and
+its output wires are poseidon2(inputs) (tests/test_gates.py).
+"""
+from typing import List, Sequence
+
+from poseidon2_constants import MAT_DIAG_M_1, RC, RC_MID
+
+P = 0xFFFF_FFFF_0000_0001
+WIDTH = 12
+ROUND_F_BEGIN = 4
+ROUND_F_END = 8
+ROUND_P = 22
+
+
+def sbox_monomial(x: int) -> int:
+    x2 = x * x % P
+    x4 = x2 * x2 % P
+    x3 = x * x2 % P
+    return x3 * x4 % P
+
+
+def matmul_m4(s: List[int]) -> None:
+    for i in range(WIDTH // 4):
+        a = 4 * i
+        t0 = (s[a] + s[a + 1]) % P
+        t1 = (s[a + 2] + s[a + 3]) % P
+        t2 = (t1 + 2 * s[a + 1]) % P          # t_1.multiply_accumulate(input[1], 2)
+        t3 = (t0 + 2 * s[a + 3]) % P
+        t4 = (t3 + 4 * t1) % P
+        t5 = (t2 + 4 * t0) % P
+        s[a], s[a + 1], s[a + 2], s[a + 3] = (t3 + t5) % P, t5, (t2 + t4) % P, t4
+
+
+def matmul_external(s: List[int]) -> None:
+    matmul_m4(s)
+    stored = [sum(s[4 * j + l] for j in range(WIDTH // 4)) % P for l in range(4)]
+    for i in range(WIDTH):
+        s[i] = (s[i] + stored[i % 4]) % P
+
+
+def matmul_internal(s: List[int]) -> None:
+    total = sum(s)
+    for i in range(WIDTH):
+        s[i] = ((MAT_DIAG_M_1[i] - 1) * s[i] + total) % P
+
+
+def poseidon2(inp: Sequence[int]) -> List[int]:
+    s = [int(x) % P for x in inp]
+    matmul_external(s)
+    for r in range(ROUND_F_BEGIN):
+        s = [sbox_monomial((s[i] + RC[r][i]) % P) for i in range(WIDTH)]
+        matmul_external(s)
+    for r in range(ROUND_P):
+        s[0] = sbox_monomial((s[0] + RC_MID[r]) % P)
+        matmul_internal(s)
+    for r in range(ROUND_F_BEGIN, ROUND_F_END):
+        s = [sbox_monomial((s[i] + RC[r][i]) % P) for i in range(WIDTH)]
+        matmul_external(s)
+    return s
+
+
+# ---- Poseidon2Gate -------------------------------------------------------------------------------------------------------------
+WIRE_SWAP = 2 * WIDTH
+START_DELTA = 2 * WIDTH + 1
+START_ROUND_F_BEGIN = START_DELTA + 4
+START_PARTIAL = START_ROUND_F_BEGIN + WIDTH * (ROUND_F_BEGIN - 1)
+START_ROUND_F_END = START_PARTIAL + ROUND_P
+POSEIDON2_NUM_WIRES = START_ROUND_F_END + WIDTH * ROUND_F_BEGIN                         # 135
+POSEIDON2_NUM_CONSTRAINTS = WIDTH * (ROUND_F_END - 1) + ROUND_P + WIDTH + 1 + 4         # 123
+
+
+def wire_input(i): return i
+def wire_output(i): return WIDTH + i
+def wire_delta(i): return START_DELTA + i
+def wire_full_round_begin(r, i): return START_ROUND_F_BEGIN + WIDTH * (r - 1) + i
+def wire_partial_round(r): return START_PARTIAL + r
+def wire_full_round_end(r, i): return START_ROUND_F_END + WIDTH * r + i
+
+
+def poseidon2_gate_eval(w: Sequence[int]) -> List[int]:
+    """eval_unfiltered_base_one: the 123 constraint values of one row (all zero iff the row is a valid Poseidon2 evaluation)"""
+    w = [int(x) % P for x in w]
+    c = []
+    swap = w[WIRE_SWAP]
+    c.append(swap * (swap - 1) % P)
+    for i in range(4):
+        c.append((swap * (w[wire_input(i + 4)] - w[wire_input(i)]) - w[wire_delta(i)]) % P)
+    s = [0] * WIDTH
+    for i in range(4):
+        d = w[wire_delta(i)]
+        s[i] = (w[wire_input(i)] + d) % P
+        s[i + 4] = (w[wire_input(i + 4)] - d) % P
+    for i in range(8, WIDTH):
+        s[i] = w[wire_input(i)]
+    matmul_external(s)
+    for r in range(ROUND_F_BEGIN):
+        s = [(s[i] + RC[r][i]) % P for i in range(WIDTH)]
+        if r != 0:
+            for i in range(WIDTH):
+                sbox_in = w[wire_full_round_begin(r, i)]
+                c.append((s[i] - sbox_in) % P)
+                s[i] = sbox_in
+        s = [sbox_monomial(x) for x in s]
+        matmul_external(s)
+    for r in range(ROUND_P):
+        s[0] = (s[0] + RC_MID[r]) % P
+        sbox_in = w[wire_partial_round(r)]
+        c.append((s[0] - sbox_in) % P)
+        s[0] = sbox_monomial(sbox_in)
+        matmul_internal(s)
+    for r in range(ROUND_F_BEGIN, ROUND_F_END):
+        s = [(s[i] + RC[r][i]) % P for i in range(WIDTH)]
+        for i in range(WIDTH):
+            sbox_in = w[wire_full_round_end(r - ROUND_F_BEGIN, i)]
+            c.append((s[i] - sbox_in) % P)
+            s[i] = sbox_in
+        s = [sbox_monomial(x) for x in s]
+        matmul_external(s)
+    for i in range(WIDTH):
+        c.append((s[i] - w[wire_output(i)]) % P)
+    assert len(c) == POSEIDON2_NUM_CONSTRAINTS
+    return c
+
+
+def poseidon2_gate_witness(inputs: Sequence[int], swap: int) -> List[int]:
+    """Poseidon2Generator::run_once: the full 135-wire row from the 12 inputs and the swap flag"""
+    w = [0] * POSEIDON2_NUM_WIRES
+    s = [int(x) % P for x in inputs]
+    for i in range(WIDTH):
+        w[wire_input(i)] = s[i]
+    w[WIRE_SWAP] = swap
+    for i in range(4):
+        w[wire_delta(i)] = swap * (s[i + 4] - s[i]) % P
+    if swap == 1:
+        for i in range(4):
+            s[i], s[i + 4] = s[i + 4], s[i]
+    matmul_external(s)
+    for r in range(ROUND_F_BEGIN):
+        s = [(s[i] + RC[r][i]) % P for i in range(WIDTH)]
+        if r != 0:
+            for i in range(WIDTH):
+                w[wire_full_round_begin(r, i)] = s[i]
+        s = [sbox_monomial(x) for x in s]
+        matmul_external(s)
+    for r in range(ROUND_P):
+        s[0] = (s[0] + RC_MID[r]) % P
+        w[wire_partial_round(r)] = s[0]
+        s[0] = sbox_monomial(s[0])
+        matmul_internal(s)
+    for r in range(ROUND_F_BEGIN, ROUND_F_END):
+        s = [(s[i] + RC[r][i]) % P for i in range(WIDTH)]
+        for i in range(WIDTH):
+            w[wire_full_round_end(r - ROUND_F_BEGIN, i)] = s[i]
+        s = [sbox_monomial(x) for x in s]
+        matmul_external(s)
+    for i in range(WIDTH):
+        w[wire_output(i)] = s[i]
+    return w
+
+
+# ---- U32ArithmeticGate (num_ops = 3 at 135 wires / 80 routed) ---------------------------------------------------------------------------
+U32_LIMB_BITS = 2
+U32_NUM_LIMBS = 64 // U32_LIMB_BITS
+U32_ROUTED_PER_OP = 6
+
+
+def u32_arith_num_ops(num_wires=135, num_routed=80):
+    return min(num_wires // (U32_ROUTED_PER_OP + U32_NUM_LIMBS), num_routed // U32_ROUTED_PER_OP)
+
+
+def u32_arithmetic_eval(w: Sequence[int], num_ops: int = 3) -> List[int]:
+    w = [int(x) % P for x in w]
+    c = []
+    for i in range(num_ops):
+        m0, m1, addend = w[6 * i], w[6 * i + 1], w[6 * i + 2]
+        out_lo, out_hi, inverse = w[6 * i + 3], w[6 * i + 4], w[6 * i + 5]
+        computed = (m0 * m1 + addend) % P
+        diff = (0xFFFFFFFF - out_hi) % P
+        hi_not_max = (inverse * diff - 1) % P
+        c.append(hi_not_max * out_lo % P)
+        combined = (out_hi * (1 << 32) + out_lo) % P
+        c.append((combined - computed) % P)
+        lo = hi = 0
+        for j in reversed(range(U32_NUM_LIMBS)):
+            limb = w[U32_ROUTED_PER_OP * num_ops + U32_NUM_LIMBS * i + j]
+            prod = 1
+            for x in range(1 << U32_LIMB_BITS):
+                prod = prod * (limb - x) % P
+            c.append(prod)
+            if j < U32_NUM_LIMBS // 2:
+                lo = ((1 << U32_LIMB_BITS) * lo + limb) % P
+            else:
+                hi = ((1 << U32_LIMB_BITS) * hi + limb) % P
+        c.append((lo - out_lo) % P)
+        c.append((hi - out_hi) % P)
+    assert len(c) == num_ops * (4 + U32_NUM_LIMBS)
+    return c
+
+
+def u32_arithmetic_witness(ops: Sequence[Sequence[int]], num_wires: int = 135) -> List[int]:
+    """ops: num_ops triples (multiplicand_0, multiplicand_1, addend) of u32 values -> the full row (U32ArithmeticGenerator::run_once)"""
+    num_ops = len(ops)
+    w = [0] * num_wires
+    for i, (m0, m1, a) in enumerate(ops):
+        out = m0 * m1 + a
+        lo, hi = out & 0xFFFFFFFF, out >> 32
+        w[6 * i:6 * i + 5] = [m0, m1, a, lo, hi]
+        w[6 * i + 5] = pow((0xFFFFFFFF - hi) % P, P - 2, P)          # inverse of (u32::MAX - output_high); 0 when that is 0
+        for j in range(U32_NUM_LIMBS):
+            w[U32_ROUTED_PER_OP * num_ops + U32_NUM_LIMBS * i + j] = (out >> (U32_LIMB_BITS * j)) & ((1 << U32_LIMB_BITS) - 1)
+    return w
+
+
+def reduce_with_powers(terms: Sequence[int], alpha: int, start_power: int = 0) -> int:
+    acc, pw = 0, pow(alpha, start_power, P)
+    for t in terms:
+        acc = (acc + t * pw) % P
+        pw = pw * alpha % P
+    return acc

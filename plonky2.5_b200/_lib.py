@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libgl_commit.so")
 
 GL_OK, GL_ERR_INVALID, GL_ERR_CUDA, GL_ERR_OOM, GL_ERR_HANDLE, GL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 GL_PART_COEFFS, GL_PART_LEAVES, GL_PART_DIGESTS, GL_PART_CAP = 0, 1, 2, 3
+GL_GATE_POSEIDON2, GL_GATE_U32_ARITHMETIC = 0, 1
 STAGES = ("h2d", "transpose", "intt", "lde", "leaf_hash", "tree", "d2h")
 
 
@@ -55,6 +56,15 @@ SIGNATURES = {
     "gl_openings_lde": (c_int, [c_void_p, c_uint64, c_uint32, c_uint32, POINTER(c_uint64)]),
     "gl_openings_end": (c_int, [c_void_p, c_uint64]),
     "gl_fri_read": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "gl_gate_num_wires": (c_int, [c_int, c_uint32]),
+    "gl_gate_num_constraints": (c_int, [c_int, c_uint32]),
+    "gl_gate_eval_rows": (c_int, [c_void_p, c_int, c_uint32, c_void_p, c_uint64, c_void_p]),
+    "gl_quotient_begin": (c_int, [c_void_p, c_uint64, c_uint32, POINTER(c_uint64)]),
+    "gl_quotient_add_gate": (c_int, [c_void_p, c_uint64, c_int, c_uint32, c_void_p, c_uint32, c_uint64, c_uint32]),
+    "gl_quotient_read": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "gl_quotient_end": (c_int, [c_void_p, c_uint64]),
+    "gl_ctx_aux_ms": (c_int, [c_void_p, POINTER(c_float)]),
+    "gl_poseidon2_gate_witness": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     "gl_fri_pow": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, POINTER(c_uint64)]),
     "gl_poseidon_permute": (c_int, [c_void_p, c_void_p, c_uint64]),
     "gl_dev_commit": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_int, c_void_p,

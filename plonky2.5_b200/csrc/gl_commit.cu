@@ -22,6 +22,7 @@
 
 #include "../../include/gl_commit.h"
 #include "fri.cuh"
+#include "gates.cuh"
 #include "merkle.cuh"
 #include "microbench.cuh"
 #include "ntt.cuh"
@@ -158,6 +159,13 @@ struct Fri {
     DevBuf coeffs, values, tmp;   // values are kept in bit-reversed order (what the next layer's leaves need)
 };
 
+struct Quotient {
+    gl_handle wires = 0;
+    uint64_t n_rows = 0;
+    uint32_t n_challenges = 0;
+    DevBuf acc, powers;
+};
+
 struct Openings {
     uint32_t log_n = 0;
     DevBuf final_poly, comp, refs, pw;   // final_poly / composition: N extension elements each
@@ -179,6 +187,8 @@ struct gl_ctx {
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
     std::map<gl_handle, std::unique_ptr<Fri>> fris;
     std::map<gl_handle, std::unique_ptr<Openings>> openings;
+    std::map<gl_handle, std::unique_ptr<Quotient>> quotients;
+    float aux_ms = 0;
     gl_handle next_handle = 1;
     cudaStream_t copy_stream = nullptr;   // host->device column copies of gl_commit, overlapped with the NTTs
     // multi-GPU exchange mode of gl_*_lde_scatter (GL_SCATTER_MODE overrides; DESIGN.md §6 has the measurements):
@@ -770,6 +780,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->trees.clear();
     c->fris.clear();
     c->openings.clear();
+    c->quotients.clear();
     c->roots.clear();
     c->pass_roots.clear();
     c->lde_tables.clear();
@@ -1634,6 +1645,157 @@ int gl_fri_read(gl_ctx* c, gl_handle fh, uint64_t* out_coeffs, uint64_t* out_val
     if (out_coeffs) CUDA_CHECK(cudaMemcpyAsync(out_coeffs, f->coeffs.p, 16 * f->len, cudaMemcpyDeviceToHost, c->stream));
     if (out_values) CUDA_CHECK(cudaMemcpyAsync(out_values, f->values.p, 16 * f->len, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+// ------------------------------------------------------------------------------------------------ gates / quotient (§8f ranks 3-4)
+namespace {
+int gate_wires(int kind, uint32_t param) {
+    if (kind == GL_GATE_POSEIDON2) return gates::P2_NUM_WIRES;
+    if (kind == GL_GATE_U32_ARITHMETIC) return (int)((gates::U32_ROUTED + gates::U32_LIMBS) * param);
+    return -1;
+}
+int gate_constraints(int kind, uint32_t param) {
+    if (kind == GL_GATE_POSEIDON2) return gates::P2_NUM_CONSTRAINTS;
+    if (kind == GL_GATE_U32_ARITHMETIC) return (int)((4 + gates::U32_LIMBS) * param);
+    return -1;
+}
+void check_gate(int kind, uint32_t param) {
+    if (kind != GL_GATE_POSEIDON2 && kind != GL_GATE_U32_ARITHMETIC) GL_THROW(GL_ERR_INVALID, "unknown gate kind %d", kind);
+    if (kind == GL_GATE_U32_ARITHMETIC && (param == 0 || param > 3)) GL_THROW(GL_ERR_INVALID, "U32ArithmeticGate: num_ops must be 1..3");
+}
+Quotient* find_quotient(gl_ctx* c, gl_handle h) {
+    auto it = c->quotients.find(h);
+    if (it == c->quotients.end()) GL_THROW(GL_ERR_HANDLE, "unknown quotient handle %llu", (unsigned long long)h);
+    return it->second.get();
+}
+}  // namespace
+
+int gl_gate_num_wires(int kind, uint32_t param) { return gate_wires(kind, param); }
+int gl_gate_num_constraints(int kind, uint32_t param) { return gate_constraints(kind, param); }
+
+int gl_gate_eval_rows(gl_ctx* c, int kind, uint32_t param, const uint64_t* rows, uint64_t n_rows, uint64_t* out) {
+    GL_API_BEGIN(c)
+    check_gate(kind, param);
+    if ((!rows || !out) && n_rows) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_rows == 0) return GL_OK;
+    const uint32_t nw = (uint32_t)gate_wires(kind, param), nc = (uint32_t)gate_constraints(kind, param);
+    c->scratch.ensure(n_rows * (nw + nc));
+    uint64_t* d_rows = c->scratch.p;
+    uint64_t* d_out = d_rows + n_rows * nw;
+    CUDA_CHECK(cudaMemcpyAsync(d_rows, rows, n_rows * nw * 8, cudaMemcpyHostToDevice, c->stream));
+    gates::gate_constraints_kernel<<<(uint32_t)((n_rows + 127) / 128), 128, 0, c->stream>>>(kind, param, d_rows, nw, n_rows, nc, d_out);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, d_out, n_rows * nc * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_quotient_begin(gl_ctx* c, gl_handle wires_batch, uint32_t n_challenges, gl_handle* out_q) {
+    GL_API_BEGIN(c)
+    if (!out_q) GL_THROW(GL_ERR_INVALID, "out_quotient is NULL");
+    if (n_challenges == 0 || n_challenges > (uint32_t)gates::MAX_CHALLENGES) GL_THROW(GL_ERR_INVALID, "n_challenges must be 1..%d", gates::MAX_CHALLENGES);
+    Tree* t = find_tree(c, wires_batch);
+    auto q = std::make_unique<Quotient>();
+    q->wires = wires_batch; q->n_rows = t->n_leaves; q->n_challenges = n_challenges;
+    q->acc.ensure(q->n_rows * n_challenges);
+    q->powers.ensure((size_t)gates::MAX_CHALLENGES * gates::MAX_CONSTRAINTS);
+    CUDA_CHECK(cudaMemsetAsync(q->acc.p, 0, q->n_rows * n_challenges * 8, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    gl_handle h = c->next_handle++;
+    c->quotients[h] = std::move(q);
+    *out_q = h;
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_quotient_add_gate(gl_ctx* c, gl_handle qh, int kind, uint32_t param, const uint64_t* alphas, uint32_t constraint_offset,
+                         gl_handle filter_batch, uint32_t filter_col) {
+    GL_API_BEGIN(c)
+    Quotient* q = find_quotient(c, qh);
+    check_gate(kind, param);
+    if (!alphas) GL_THROW(GL_ERR_INVALID, "alphas is NULL");
+    Tree* t = find_tree(c, q->wires);
+    const uint32_t nw = (uint32_t)gate_wires(kind, param), nc = (uint32_t)gate_constraints(kind, param);
+    if (t->leaf_len < nw) GL_THROW(GL_ERR_INVALID, "the wires batch has %u columns, the gate needs %u", t->leaf_len, nw);
+    if (nc > (uint32_t)gates::MAX_CONSTRAINTS) GL_THROW(GL_ERR_UNSUPPORTED, "too many constraints");
+    gates::QuotientArgs a{};
+    a.rows = t->leaves.p; a.pitch = t->pitch; a.n_rows = q->n_rows; a.acc = q->acc.p; a.powers = q->powers.p;
+    a.n_constraints = nc; a.n_challenges = q->n_challenges; a.kind = (uint32_t)kind; a.param = param;
+    if (filter_batch) {
+        Tree* f = find_tree(c, filter_batch);
+        if (f->n_leaves != q->n_rows) GL_THROW(GL_ERR_INVALID, "filter batch has %llu rows, the wires batch %llu", (unsigned long long)f->n_leaves, (unsigned long long)q->n_rows);
+        if (filter_col >= f->leaf_len) GL_THROW(GL_ERR_INVALID, "filter column %u out of range", filter_col);
+        a.filter = f->leaves.p; a.filter_pitch = f->pitch; a.filter_col = filter_col;
+    }
+    // alpha_k^(offset + i): a few hundred host multiplies per call
+    std::vector<uint64_t> pw((size_t)q->n_challenges * nc);
+    for (uint32_t k = 0; k < q->n_challenges; k++) {
+        const uint64_t al = gl::canon(alphas[k]);
+        uint64_t cur = gl::h_pow(al, constraint_offset);
+        for (uint32_t i = 0; i < nc; i++) { pw[(size_t)k * nc + i] = cur; cur = gl::h_mul(cur, al); }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(q->powers.p, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t grid = (uint32_t)((q->n_rows + 127) / 128);
+    const size_t smem = pw.size() * 8;
+    CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+    switch (q->n_challenges) {
+        case 1: gates::gate_quotient_kernel<1><<<grid, 128, smem, c->stream>>>(a); break;
+        case 2: gates::gate_quotient_kernel<2><<<grid, 128, smem, c->stream>>>(a); break;
+        case 3: gates::gate_quotient_kernel<3><<<grid, 128, smem, c->stream>>>(a); break;
+        default: gates::gate_quotient_kernel<4><<<grid, 128, smem, c->stream>>>(a); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // pw is a host vector of this call
+    CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, c->ev[0], c->ev[1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_quotient_read(gl_ctx* c, gl_handle qh, uint64_t* out) {
+    GL_API_BEGIN(c)
+    Quotient* q = find_quotient(c, qh);
+    if (!out) GL_THROW(GL_ERR_INVALID, "out is NULL");
+    CUDA_CHECK(cudaMemcpyAsync(out, q->acc.p, q->n_rows * q->n_challenges * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_quotient_end(gl_ctx* c, gl_handle qh) {
+    GL_API_BEGIN(c)
+    find_quotient(c, qh);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->quotients.erase(qh);
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_ctx_aux_ms(gl_ctx* c, float* out_ms) {
+    if (!c || !out_ms) return GL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out_ms = c->aux_ms;
+    return GL_OK;
+}
+
+int gl_poseidon2_gate_witness(gl_ctx* c, const uint64_t* inputs, uint64_t n, uint64_t* out_rows) {
+    GL_API_BEGIN(c)
+    if ((!inputs || !out_rows) && n) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n == 0) return GL_OK;
+    c->scratch.ensure(n * (13 + gates::P2_NUM_WIRES));
+    uint64_t* d_in = c->scratch.p;
+    uint64_t* d_out = d_in + n * 13;
+    CUDA_CHECK(cudaMemcpyAsync(d_in, inputs, n * 13 * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+    gates::poseidon2_witness_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, c->stream>>>(d_in, n, d_out, gates::P2_NUM_WIRES);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out_rows, d_out, n * gates::P2_NUM_WIRES * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, c->ev[0], c->ev[1]));
     return GL_OK;
     GL_API_END(c)
 }

@@ -349,7 +349,8 @@ ntt_pass_kernel(const ntt::PassParams p) {
             } else {
                 // inter-pass twiddle w_{2^log_blk}^(o_lo * bitrev_A(l)), l = 16 q16 + e: bitrev_A(l) = bitrev_4(e) * 2^(A-4) + bitrev_(A-4)(q16)
                 const uint32_t N = 1u << p.log_n, sh = p.log_n - p.log_blk;
-                const uint32_t ex0 = (o_lo * gl::bitrev32(q16, A - 4)) << sh, exs = (o_lo << (A - 4)) << sh;
+                constexpr uint32_t A4 = A >= 4 ? A - 4 : 0;   // (this branch only exists for A >= 4)
+                const uint32_t ex0 = (o_lo * gl::bitrev32(q16, A4)) << sh, exs = (o_lo << A4) << sh;
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
                     const uint32_t ex = ex0 + exs * brev_const(e, 4);

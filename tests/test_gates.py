@@ -1,0 +1,142 @@
+"""§8(f) ranks 3-4: the reference's own gates on the GPU — constraint evaluation over the resident LDE rows (what
+compute_quotient_polys does per gate) and Poseidon2Gate witness generation — against oracle/gates_oracle.py, a line-by-line
+restatement of Rust that IS in the reference tree (/root/reference/src/common/poseidon2/poseidon2_gate.rs:233-310, :447-523;
+/root/reference/src/common/u32/gates/arithmetic_u32.rs:103-166)."""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import gates_oracle as go
+from oracle_c import splitmix_columns
+
+P = go.P
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the oracle itself
+def test_poseidon2_constants_match_the_reference_source():
+    fix = json.load(open(os.path.join(ROOT, "tests", "golden", "poseidon2_constants.json")))
+    assert fix["MAT_DIAG_M_1"] == go.MAT_DIAG_M_1 and fix["RC"] == go.RC and fix["RC_MID"] == go.RC_MID
+    assert all(0 <= x < P for row in go.RC for x in row) and all(0 <= x < P for x in go.RC_MID)
+    cuh = open(os.path.join(ROOT, "plonky2.5_b200", "csrc", "poseidon2_constants.cuh")).read()
+    for x in go.RC_MID + go.RC[3] + [d - 1 for d in go.MAT_DIAG_M_1]:
+        assert "0x%016xULL" % x in cuh
+    ref = "/root/reference/src/common/poseidon2/poseidon2_goldilocks.rs"
+    if os.path.exists(ref):                              # build container only
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gen_p2", os.path.join(ROOT, "tools", "gen_poseidon2_constants.py"))
+        gen = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(gen)
+        c = gen.parse(ref)
+        assert c["MAT_DIAG_M_1"] == go.MAT_DIAG_M_1 and c["RC"] == go.RC and c["RC_MID"] == go.RC_MID
+
+
+def test_gate_oracle_consistency():
+    """rows filled by the generators satisfy every constraint; outputs are the permutation; tampering any wire breaks a constraint"""
+    rnd = random.Random(5)
+    assert go.POSEIDON2_NUM_WIRES == 135 and go.POSEIDON2_NUM_CONSTRAINTS == 123
+    for swap in (0, 1):
+        x = [rnd.randrange(P) for _ in range(12)]
+        w = go.poseidon2_gate_witness(x, swap)
+        assert not any(go.poseidon2_gate_eval(w))
+        assert w[12:24] == go.poseidon2(x[4:8] + x[0:4] + x[8:12] if swap else x)
+        for i in rnd.sample(range(135), 20):
+            t = list(w)
+            t[i] = (t[i] + 1) % P
+            assert any(go.poseidon2_gate_eval(t)), i
+    assert go.u32_arith_num_ops() == 3
+    ops = [(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF), (0, 5, 7), (rnd.getrandbits(32), rnd.getrandbits(32), rnd.getrandbits(32))]
+    w = go.u32_arithmetic_witness(ops)
+    assert len(go.u32_arithmetic_eval(w)) == 108 and not any(go.u32_arithmetic_eval(w))
+    w[3] ^= 1
+    assert any(go.u32_arithmetic_eval(w))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _rows(kind, n, seed):
+    """n x 135 rows: valid gate rows, valid rows with one wire tampered, and arbitrary field elements (incl. non-canonical words)"""
+    rnd = random.Random(seed)
+    rows = []
+    for r in range(n):
+        m = r % 3
+        if kind == 0:
+            w = go.poseidon2_gate_witness([rnd.randrange(P) for _ in range(12)], rnd.randrange(2))
+        else:
+            w = go.u32_arithmetic_witness([(rnd.getrandbits(32), rnd.getrandbits(32), rnd.getrandbits(32)) for _ in range(3)])
+        if m == 1:
+            w[rnd.randrange(len(w))] = rnd.randrange(P)
+        if m == 2:
+            w = [rnd.getrandbits(64) for _ in range(135)]
+        rows.append(w)
+    return np.array(rows, dtype=np.uint64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,param", [(0, 0), (1, 3), (1, 1)])
+def test_gate_constraints_match_oracle(ctx, kind, param):
+    lib = ctx.lib
+    nw, nc = lib.gl_gate_num_wires(kind, param), lib.gl_gate_num_constraints(kind, param)
+    assert (nw, nc) == ((135, 123) if kind == 0 else (38 * param, 36 * param))
+    rows = _rows(kind, 96, 40 + kind)[:, :nw].copy()
+    if kind == 1 and param == 1:
+        rows = np.array([go.u32_arithmetic_witness([(7, 9, 11)], num_wires=38), [random.Random(3).getrandbits(64) for _ in range(38)]], dtype=np.uint64)
+    out = np.zeros((rows.shape[0], nc), dtype=np.uint64)
+    assert lib.gl_gate_eval_rows(ctx.handle, kind, param, rows.ctypes.data, rows.shape[0], out.ctypes.data) == 0
+    for r in range(rows.shape[0]):
+        want = go.poseidon2_gate_eval(rows[r].tolist()) if kind == 0 else go.u32_arithmetic_eval(rows[r].tolist(), num_ops=param)
+        assert out[r].tolist() == want, r
+
+
+@pytest.mark.gpu
+def test_poseidon2_gate_witness_matches_generator(ctx):
+    rnd = random.Random(9)
+    inp = np.array([[rnd.randrange(P) for _ in range(12)] + [rnd.randrange(2)] for _ in range(64)], dtype=np.uint64)
+    inp[5, :12] = np.uint64(P - 1)
+    inp[6, :12] = 0
+    out = np.zeros((64, 135), dtype=np.uint64)
+    assert ctx.lib.gl_poseidon2_gate_witness(ctx.handle, inp.ctypes.data, 64, out.ctypes.data) == 0
+    for r in range(64):
+        assert out[r].tolist() == go.poseidon2_gate_witness(inp[r, :12].tolist(), int(inp[r, 12])), r
+    # and the generated rows satisfy the gate on the device
+    c = np.zeros((64, 123), dtype=np.uint64)
+    assert ctx.lib.gl_gate_eval_rows(ctx.handle, 0, 0, out.ctypes.data, 64, c.ctypes.data) == 0
+    assert not c.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n,n_ch", [(5, 2), (9, 2), (7, 1)])
+def test_quotient_accumulation_over_resident_lde_rows(ctx, log_n, n_ch):
+    """commit a wires batch, then accumulate both gates' alpha-combined constraints over its R = 8N LDE rows (with a filter column for
+    the second gate): every row equals reduce_with_powers of the oracle's constraint values of that leaf row."""
+    import plonky25_b200 as g
+    lib, r = ctx.lib, 3
+    n = 1 << log_n
+    wires = g.PolynomialBatch.from_values(list(splitmix_columns(70 + log_n, 135, n)), r, False, 0, ctx=ctx)
+    consts = g.PolynomialBatch.from_values(list(splitmix_columns(71 + log_n, 4, n)), r, False, 0, ctx=ctx)
+    R = n << r
+    alphas = np.array([0x123456789ABCDEF % P, P - 2, 5, 0][:n_ch], dtype=np.uint64)
+    q = ctypes.c_uint64()
+    assert lib.gl_quotient_begin(ctx.handle, wires.merkle_tree._h, n_ch, ctypes.byref(q)) == 0
+    assert lib.gl_quotient_add_gate(ctx.handle, q.value, 0, 0, alphas.ctypes.data, 0, 0, 0) == 0
+    assert lib.gl_quotient_add_gate(ctx.handle, q.value, 1, 3, alphas.ctypes.data, 123, consts.merkle_tree._h, 2) == 0
+    out = np.zeros((n_ch, R), dtype=np.uint64)
+    assert lib.gl_quotient_read(ctx.handle, q.value, out.ctypes.data) == 0
+    assert lib.gl_quotient_end(ctx.handle, q.value) == 0
+    rnd = random.Random(log_n)
+    rows = sorted(set([0, 1, R - 1] + [rnd.randrange(R) for _ in range(24)]))
+    lw, lc = wires.merkle_tree.open_batch(rows)[0], consts.merkle_tree.open_batch(rows)[0]
+    for j, row in enumerate(rows):
+        c0 = go.poseidon2_gate_eval(lw[j].tolist())
+        c1 = go.u32_arithmetic_eval(lw[j].tolist()[:114], num_ops=3)
+        f = int(lc[j][2])
+        for k in range(n_ch):
+            a = int(alphas[k])
+            want = (go.reduce_with_powers(c0, a) + f * go.reduce_with_powers(c1, a, start_power=123)) % P
+            assert int(out[k, row]) == want, (row, k)
+    with pytest.raises(Exception):
+        assert lib.gl_quotient_add_gate(ctx.handle, 12345, 0, 0, alphas.ctypes.data, 0, 0, 0) == 0
+    wires.merkle_tree.free(); consts.merkle_tree.free()
