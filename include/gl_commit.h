@@ -178,6 +178,19 @@ int gl_ctx_aux_ms(gl_ctx* ctx, float* out_ms);
  * inputs + the swap flag of each row -> out_rows [n][135], every wire of the row (deltas, S-box inputs of all rounds, outputs)        */
 int gl_poseidon2_gate_witness(gl_ctx* ctx, const uint64_t* inputs, uint64_t n, uint64_t* out_rows);
 
+/* ---- permutation argument: partial products and Z --------------------------------------------------------
+ * plonky2 plonk/prover.rs · all_wires_permutation_partial_products (+ the "Z first" reordering prove() applies before committing):
+ * per challenge k and row i (x_i = w_N^i):  q_ic = prod_{j in chunk c of `degree` routed wires} (wire_ij + beta_k k_j x_i + gamma_k) /
+ * (wire_ij + beta_k sigma_ij + gamma_k); a running product over (i, c) from Z(x_0) = 1 gives the partial products and Z(x_{i+1}).
+ * wire_cols / sigma_cols: n_routed host pointers each, N = 2^log_n words (witness wire values; sigma polynomial VALUES on the subgroup,
+ * i.e. prover_data.sigmas transposed); k_is: the n_routed coset shifts (get_unique_coset_shifts: 7^j).
+ * out_cols: [(n_challenges * n_chunks)][N] words, n_chunks = ceil(n_routed / degree): first the Z polynomial of every challenge, then
+ * the n_chunks - 1 partial products of challenge 0, of challenge 1, ... — the column order of the Z/partial-products commit.
+ * Upstream source is not in /root/reference: restated (parity unpinned), see plonky2.5_b200/csrc/permutation.cuh.                     */
+int gl_partial_products(gl_ctx* ctx, const uint64_t* const* wire_cols, const uint64_t* const* sigma_cols, uint32_t n_routed, uint32_t log_n,
+                        const uint64_t* k_is, const uint64_t* betas, const uint64_t* gammas, uint32_t n_challenges, uint32_t degree,
+                        uint64_t* out_cols);
+
 /* ---- FRI proof of work: fri_proof_of_work  (plonky2 fri/prover.rs) ---------------------------------------------
  * sponge_state / input_buffer: the caller's Challenger fields (sponge_state, pending input_buffer, n_inputs < 8).
  * Finds the SMALLEST canonical w such that, with the pending inputs written into the state and w in the next input

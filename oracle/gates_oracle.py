@@ -237,3 +237,43 @@ def reduce_with_powers(terms: Sequence[int], alpha: int, start_power: int = 0) -
         acc = (acc + t * pw) % P
         pw = pw * alpha % P
     return acc
+
+
+# ---- permutation argument: partial products and Z (plonky2 plonk/prover.rs · wires_permutation_partial_products_and_zs) -------------
+# Upstream source is NOT under /root/reference (plonky2 @ 3de92d9, un-vendored): restated from the published algorithm — parity
+# unpinned.  The independent check is the defining identity of the argument (tests/test_gates.py): for wires that satisfy a copy
+# permutation sigma, Z closes (the running product returns to 1 after the last row).
+def partial_products_and_zs(wires, sigmas, k_is, betas, gammas, degree, log_n):
+    """wires / sigmas: [n_routed][N] columns (values on the subgroup, natural order).  Returns the polynomials in prove()'s order:
+    [Z_0, .., Z_{c-1}, pp_0 of challenge 0, .., pp of challenge c-1 ..], each a list of N values."""
+    n_routed, n = len(wires), 1 << log_n
+    w = pow(1753635133440165772, 1 << (32 - log_n), P)
+    xs = [pow(w, i, P) for i in range(n)]
+    n_chunks = -(-n_routed // degree)
+    zs, pps = [], []
+    for beta, gamma in zip(betas, gammas):
+        z_x = 1
+        z_col, pp_cols = [], [[] for _ in range(n_chunks - 1)]
+        for i in range(n):
+            quotients = []
+            for j in range(n_routed):
+                num = (wires[j][i] + beta * k_is[j] % P * xs[i] + gamma) % P
+                den = (wires[j][i] + beta * sigmas[j][i] + gamma) % P
+                quotients.append(num * pow(den, P - 2, P) % P)
+            chunk_products = []
+            for c in range(n_chunks):
+                prod = 1
+                for q in quotients[c * degree:(c + 1) * degree]:
+                    prod = prod * q % P
+                chunk_products.append(prod)
+            acc, res = z_x, []
+            for q in chunk_products:                      # partial_products_and_z_gx
+                acc = acc * q % P
+                res.append(acc)
+            z_col.append(z_x)                             # "the last term is Z(gx), but we replace it with Z(x)"
+            z_x = res[-1]
+            for c in range(n_chunks - 1):
+                pp_cols[c].append(res[c])
+        zs.append(z_col)
+        pps.extend(pp_cols)
+    return zs + pps

@@ -28,6 +28,7 @@
 #include "ntt.cuh"
 #include "ntt2.cuh"
 #include "openings.cuh"
+#include "permutation.cuh"
 
 namespace {
 
@@ -1794,6 +1795,64 @@ int gl_poseidon2_gate_witness(gl_ctx* c, const uint64_t* inputs, uint64_t n, uin
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
     CUDA_CHECK(cudaMemcpyAsync(out_rows, d_out, n * gates::P2_NUM_WIRES * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, c->ev[0], c->ev[1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_partial_products(gl_ctx* c, const uint64_t* const* wire_cols, const uint64_t* const* sigma_cols, uint32_t n_routed, uint32_t log_n,
+                        const uint64_t* k_is, const uint64_t* betas, const uint64_t* gammas, uint32_t n_ch, uint32_t degree, uint64_t* out_cols) {
+    GL_API_BEGIN(c)
+    if (!wire_cols || !sigma_cols || !k_is || !betas || !gammas || !out_cols) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_routed == 0 || degree == 0) GL_THROW(GL_ERR_INVALID, "n_routed and degree must be positive");
+    if (n_ch == 0 || n_ch > 4) GL_THROW(GL_ERR_INVALID, "n_challenges must be 1..4");
+    if (log_n > 28) GL_THROW(GL_ERR_UNSUPPORTED, "log_n = %u > 28", log_n);
+    const uint32_t n_chunks = (n_routed + degree - 1) / degree;
+    if (n_chunks > (uint32_t)perm::MAX_CHUNKS) GL_THROW(GL_ERR_UNSUPPORTED, "more than %d chunks (n_routed / degree)", perm::MAX_CHUNKS);
+    for (uint32_t j = 0; j < n_routed; j++)
+        if (!wire_cols[j] || !sigma_cols[j]) GL_THROW(GL_ERR_INVALID, "column %u is NULL", j);
+    const uint64_t N = 1ULL << log_n;
+    const uint32_t pitch = round_up(n_routed, 8);
+    // layout of the scratch: wires [N][pitch] | sigmas [N][pitch] | xs [N] | k_is | q [n_ch][N][n_chunks] | out [n_ch*n_chunks][N]
+    const size_t w_words = N * pitch, q_words = (size_t)n_ch * N * n_chunks;
+    c->in_stage.ensure(2 * N * n_routed);
+    c->scratch.ensure(2 * w_words + N + round_up(n_routed, 8) + 2 * q_words);
+    uint64_t* d_w = c->scratch.p;
+    uint64_t* d_s = d_w + w_words;
+    uint64_t* d_x = d_s + w_words;
+    uint64_t* d_k = d_x + N;
+    uint64_t* d_q = d_k + round_up(n_routed, 8);
+    uint64_t* d_out = d_q + q_words;
+    for (uint32_t j = 0; j < n_routed; j++) {
+        CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)j * N, wire_cols[j], N * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + (uint64_t)(n_routed + j) * N, sigma_cols[j], N * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<uint64_t> kk(n_routed);
+    for (uint32_t j = 0; j < n_routed; j++) kk[j] = gl::canon(k_is[j]);
+    CUDA_CHECK(cudaMemcpyAsync(d_k, kk.data(), n_routed * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+    dim3 tb(32, 8), tg((uint32_t)((N + 31) / 32), (pitch + 31) / 32);
+    ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(c->in_stage.p, N, d_w, pitch, pitch, n_routed, N);
+    ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(c->in_stage.p + (uint64_t)n_routed * N, N, d_s, pitch, pitch, n_routed, N);
+    CUDA_CHECK(cudaGetLastError());
+    {
+        ntt::PowTable pt{};
+        uint64_t sq = gl::h_root_of_unity(log_n);
+        for (uint32_t k = 0; k < 32; k++) { pt.g2k[k] = sq; sq = gl::h_mul(sq, sq); }
+        ntt::powers_kernel<<<(uint32_t)((N + 255) / 256), 256, 0, c->stream>>>(d_x, N, pt);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    perm::Args a{};
+    a.wires = d_w; a.sigmas = d_s; a.k_is = d_k; a.xs = d_x; a.q = d_q; a.out = d_out;
+    for (uint32_t k = 0; k < n_ch; k++) { a.beta[k] = gl::canon(betas[k]); a.gamma[k] = gl::canon(gammas[k]); }
+    a.n = (uint32_t)N; a.pitch = pitch; a.n_routed = n_routed; a.degree = degree; a.n_chunks = n_chunks; a.n_ch = n_ch;
+    perm::chunk_quotients_kernel<<<dim3((uint32_t)((N + 127) / 128), n_ch), 128, 0, c->stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    perm::running_product_kernel<<<n_ch, 1024, 0, c->stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out_cols, d_out, q_words * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, c->ev[0], c->ev[1]));
     return GL_OK;

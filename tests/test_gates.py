@@ -140,3 +140,53 @@ def test_quotient_accumulation_over_resident_lde_rows(ctx, log_n, n_ch):
     with pytest.raises(Exception):
         assert lib.gl_quotient_add_gate(ctx.handle, 12345, 0, 0, alphas.ctypes.data, 0, 0, 0) == 0
     wires.merkle_tree.free(); consts.merkle_tree.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n,n_routed,degree,n_ch", [(4, 80, 8, 2), (6, 80, 8, 2), (5, 13, 4, 1), (3, 8, 8, 3)])
+def test_partial_products_and_zs_match_oracle(ctx, log_n, n_routed, degree, n_ch):
+    """gl_partial_products against the restated wires_permutation_partial_products_and_zs; and the argument's own identity: when the
+    wires satisfy a copy permutation sigma, the running product closes (Z(x_0) = 1 and the product over all rows is 1 again)."""
+    rnd = random.Random(100 + log_n)
+    n = 1 << log_n
+    w = pow(1753635133440165772, 1 << (32 - log_n), P)
+    xs = [pow(w, i, P) for i in range(n)]
+    k_is = [pow(7, j, P) for j in range(n_routed)]
+    # a copy permutation on the (column, row) grid made of a few cycles; wires constant on every cycle
+    cells = [(j, i) for j in range(n_routed) for i in range(n)]
+    perm = list(range(len(cells)))
+    rnd.shuffle(perm)
+    sigma_of = {}
+    wires = [[0] * n for _ in range(n_routed)]
+    cycle_len = 5
+    for c0 in range(0, len(perm), cycle_len):
+        cyc = [cells[t] for t in perm[c0:c0 + cycle_len]]
+        v = rnd.randrange(P)
+        for a, b in zip(cyc, cyc[1:] + cyc[:1]):
+            sigma_of[a] = b
+            wires[a[0]][a[1]] = v
+    sigmas = [[k_is[sigma_of[(j, i)][0]] * xs[sigma_of[(j, i)][1]] % P for i in range(n)] for j in range(n_routed)]
+    betas = [rnd.randrange(P) for _ in range(n_ch)]
+    gammas = [rnd.randrange(P) for _ in range(n_ch)]
+    want = go.partial_products_and_zs(wires, sigmas, k_is, betas, gammas, degree, log_n)
+    n_chunks = -(-n_routed // degree)
+    W, S = np.array(wires, dtype=np.uint64), np.array(sigmas, dtype=np.uint64)
+    W[0, 0] += np.uint64(P) if int(W[0, 0]) < 2**32 - 1 else np.uint64(0)     # a non-canonical input word
+    out = np.zeros((n_ch * n_chunks, n), dtype=np.uint64)
+    wp_ = (ctypes.c_void_p * n_routed)(*[W[j].ctypes.data for j in range(n_routed)])
+    sp_ = (ctypes.c_void_p * n_routed)(*[S[j].ctypes.data for j in range(n_routed)])
+    k = np.array(k_is, dtype=np.uint64); b = np.array(betas, dtype=np.uint64); gm = np.array(gammas, dtype=np.uint64)
+    rc = ctx.lib.gl_partial_products(ctx.handle, wp_, sp_, n_routed, log_n, k.ctypes.data, b.ctypes.data, gm.ctypes.data, n_ch, degree,
+                                     out.ctypes.data)
+    assert rc == 0, ctx.lib.gl_ctx_last_error(ctx.handle).decode()
+    assert out.tolist() == want
+    # the permutation argument closes: Z(x_0) = 1 and Z(x_{n-1}) * (last row's chunk products) = 1
+    for c in range(n_ch):
+        assert int(out[c, 0]) == 1
+        last = int(out[c, n - 1])
+        acc = last
+        for j in range(n_routed):
+            num = (wires[j][n - 1] + betas[c] * k_is[j] % P * xs[n - 1] + gammas[c]) % P
+            den = (wires[j][n - 1] + betas[c] * sigmas[j][n - 1] + gammas[c]) % P
+            acc = acc * num % P * pow(den, P - 2, P) % P
+        assert acc == 1
