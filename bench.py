@@ -10,9 +10,12 @@ the shape the metric is quoted on; it fits one GPU).  `value` is measured with t
 (gl_dev_commit / the sharded device path), `e2e` through the reference-facing C ABI call gl_commit with host buffers
 (pinned), i.e. including the host->device copy of the inputs and the device->host read of the Merkle cap, every step.
 
-N > 1: the batch is sharded by polynomial column for the iNTT/LDE, exchanged column->row with one NCCL all-to-all, and
-every rank hashes whole cap subtrees of its contiguous leaf range; the subtree roots are all-gathered into the cap
-(SURVEY.md §8e).  Per-rank work shrinks with N ("strong" scaling of one commit).
+N > 1 (one process per GPU, torchrun): columns are sharded for the iNTT; the ranks exchange coefficient blocks over NVLink (one
+contiguous peer copy per block, overlapped with the NTTs) and every rank evaluates only the LDE cosets whose leaf rows it owns, for
+all columns (--exchange coset, the default when N <= 2^rate_bits; p2p / nccl = the column->row shipment of the LDE output by the
+copy engines / by an NCCL all-to-all); every rank hashes whole cap subtrees of its contiguous leaf range and the subtree roots are
+all-gathered into the cap.  Per-rank work shrinks with N ("strong" scaling of one commit).  --single-process drives
+the N GPUs from one process through gl_commit_multi.
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, C + OpenMP, all host threads) on a
 bounded sample of the same workload; the reference itself is Rust + an un-vendored crate and cannot be built here
@@ -52,7 +55,9 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=17, help="rows (log2) of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="multi-GPU column->row exchange (DESIGN.md §6)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "coset", "p2p", "nccl"],
+                    help="multi-GPU plan (DESIGN.md §6): coset = exchange coefficients, every rank evaluates its own cosets (default when "
+                         "N <= 2^rate_bits); p2p = column->row shipment of the LDE output by the copy engines; nccl = all-to-all baseline")
     ap.add_argument("--workload", default="commit", choices=["commit", "wrapper"],
                     help="commit: the headline PolynomialBatch commit; wrapper: the wrapper-circuit-shaped prove pipeline (commits 86/135/20/16 "
                          "x 2^16 -> prove_openings -> FRI [4,4,4] -> PoW 16 -> 28 query rounds), second line of BASELINE.json's metric")
@@ -531,10 +536,13 @@ def main():
             dist.all_reduce(hb)
             h2d = int(hb.item())
         parity["e2e_cap_equals_device_cap"] = bool(np.array_equal(cap, cap_dev))
+        e2e_stage_ms, _ = ctx.stage_times()
         e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "stage_ms_last_call_rank0": {k: round(v, 3) for k, v in e2e_stage_ms.items() if v},
                "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
-                      if world == 1 else "ShardedCommit.commit_host: pinned host shard -> gl_lde_scatter (chunked H2D overlapped with the NTTs) -> hash -> cap to host"}
+                      if world == 1 else "ShardedCommit.commit_host: pinned host shard -> gl_lde_scatter (chunked H2D overlapped with the NTTs) -> hash -> cap to host; plan: "
+                      + (state._host_impl.exchange if state._host_impl is not None else state.exchange)}
 
     if world > 1:
         if os.environ.get("GL_BENCH_PHASES"):
@@ -617,9 +625,10 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer + exact fp64 limb arithmetic)", "data": "synthetic",
             "config": {"workload": workload_name(a), "log_n": log_n, "n_cols": cols, "rate_bits": r, "cap_height": h,
-                       "sharding": "none" if world == 1 else (f"columns/{world} -> " + ("NTT stores into peer leaf buffers over NVLink (fused)"
-                                                                                  if state.exchange == "p2p" else "NCCL all-to-all + repack")
-                                                             + f" -> leaf ranges/{world}"),
+                       "sharding": "none" if world == 1 else (f"columns/{world} -> " + {
+                           "coset": "iNTT -> coefficient blocks pulled over NVLink (one contiguous copy per peer, overlapped with the NTTs) -> own cosets of all columns",
+                           "p2p": "LDE -> coset rows shipped to their owners by the copy engines behind the next coset's NTT",
+                           "nccl": "LDE -> NCCL all-to-all + repack"}[state.exchange] + f" -> leaf ranges/{world}"),
                        "l2": "inputs (%.2f GB) and leaves (%.2f GB) exceed the 126 MB L2; no flush needed" % (cols * n * 8 / 1e9, R * cols * 8 / 1e9),
                        "permutations_per_step": perms_per_commit(log_n, cols, r, h)},
             "stage_ms": {k: round(v / a.steps, 4) for k, v in stage_acc.items()},

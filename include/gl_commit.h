@@ -171,6 +171,12 @@ int gl_quotient_begin(gl_ctx* ctx, gl_handle wires_batch, uint32_t n_challenges,
 int gl_quotient_add_gate(gl_ctx* ctx, gl_handle quotient, int kind, uint32_t param, const uint64_t* alphas, uint32_t constraint_offset,
                          gl_handle filter_batch, uint32_t filter_col);
 int gl_quotient_read(gl_ctx* ctx, gl_handle quotient, uint64_t* out);
+/* the tail of compute_quotient_polys and the quotient commit of prove() (plonky2 plonk/prover.rs), without leaving the device:
+ * acc_k / Z_H on the coset (ZeroPolyOnCoset::eval_inverse), coset_ifft(7) to coefficients (degree < 2^rate_bits * N), split into
+ * 2^rate_bits chunks of N coefficients each (quotient_degree_factor = 2^rate_bits, the reference's configuration), and
+ * PolynomialBatch::from_coeffs of the n_challenges * 2^rate_bits chunk polynomials (challenge-major).  out_cap: 2^cap_height * 4 words;
+ * out_batch: the committed batch (coefficients, leaves, digests resident), as from gl_commit.  Restated from upstream (parity unpinned).  */
+int gl_quotient_commit(gl_ctx* ctx, gl_handle quotient, uint32_t cap_height, uint64_t* out_cap, gl_handle* out_batch);
 int gl_quotient_end(gl_ctx* ctx, gl_handle quotient);
 /* CUDA-event milliseconds of the last gl_quotient_add_gate / gl_poseidon2_gate_witness kernel on this context */
 int gl_ctx_aux_ms(gl_ctx* ctx, float* out_ms);
@@ -228,6 +234,24 @@ int gl_dev_lde_scatter(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride,
 int gl_lde_scatter(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
                    int input_is_coeffs, uint64_t* const* peer_leaves, uint32_t n_peers, uint32_t leaf_pitch, uint32_t col_off,
                    uint64_t* d_out_coeffs, uint32_t coeff_pitch, uint32_t first_coset);
+/* ---- coset-sharded commit (one process per GPU; the default multi-GPU plan when n_ranks <= 2^rate_bits) --------------------------------
+ * Leaf rows are stored in bit-reversed LDE order, so the contiguous leaf range a rank owns is a set of whole LDE cosets.
+ * Instead of exchanging LDE OUTPUT column->row (R x C words in 8C/G-byte pieces), the ranks exchange COEFFICIENTS: every rank runs the
+ * iNTT of its column shard (gl_dev_intt), pulls the other ranks' coefficient blocks — whole contiguous [N][pitch] buffers, one large
+ * NVLink copy each, overlapped with the NTTs of the blocks that have already arrived — and evaluates only ITS OWN cosets for ALL columns,
+ * writing its leaf rows in place (gl_dev_lde_own_cosets).  Same bytes on the wire per rank (8 C N (G-1)/G), no strided shipment, no exposed
+ * tail, LDE work perfectly balanced.
+ * gl_dev_intt: d_out_coeffs [N][coeff_pitch] <- iNTT (or canonical copy if input_is_coeffs) of the n_cols device columns.
+ * gl_dev_lde_own_cosets: peer_coeffs[q] = rank q's coefficient block (own buffer for q == self, CUDA-IPC mapping otherwise), with
+ * pitches[q], col_counts[q], col_offsets[q]; d_stage[q] = local staging for rank q's block (ignored for q == self);
+ * leaf blocks [self*2^rate_bits/n_peers, (self+1)*2^rate_bits/n_peers) are written to d_leaves [rows_per_rank][leaf_pitch].
+ * The caller synchronises the ranks between the two calls (every block complete) — see plonky2.5_b200/sharded.py.                   */
+int gl_dev_intt(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, int input_is_coeffs,
+                uint64_t* d_out_coeffs, uint32_t coeff_pitch);
+int gl_dev_lde_own_cosets(gl_ctx* ctx, uint64_t* const* peer_coeffs, uint64_t* const* d_stage, const uint32_t* pitches,
+                          const uint32_t* col_counts, const uint32_t* col_offsets, uint32_t n_peers, uint32_t self, uint32_t log_n,
+                          uint32_t rate_bits, uint64_t* d_leaves, uint32_t leaf_pitch);
+
 /* CUDA IPC plumbing for the above: export a device buffer (64-byte handle) / map a peer's / unmap / free */
 int gl_dev_ipc_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]);
 int gl_dev_ipc_open(gl_ctx* ctx, const uint8_t handle[64], uint64_t** out_ptr);

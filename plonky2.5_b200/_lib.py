@@ -62,6 +62,7 @@ SIGNATURES = {
     "gl_quotient_begin": (c_int, [c_void_p, c_uint64, c_uint32, POINTER(c_uint64)]),
     "gl_quotient_add_gate": (c_int, [c_void_p, c_uint64, c_int, c_uint32, c_void_p, c_uint32, c_uint64, c_uint32]),
     "gl_quotient_read": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "gl_quotient_commit": (c_int, [c_void_p, c_uint64, c_uint32, c_void_p, POINTER(c_uint64)]),
     "gl_quotient_end": (c_int, [c_void_p, c_uint64]),
     "gl_ctx_aux_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gl_poseidon2_gate_witness": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
@@ -76,6 +77,9 @@ SIGNATURES = {
                                    c_uint32, c_uint32, c_void_p, c_uint32, c_uint32]),
     "gl_lde_scatter": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_int, POINTER(c_void_p), c_uint32,
                                c_uint32, c_uint32, c_void_p, c_uint32, c_uint32]),
+    "gl_dev_intt": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int, c_void_p, c_uint32]),
+    "gl_dev_lde_own_cosets": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32),
+                                      c_uint32, c_uint32, c_uint32, c_uint32, c_void_p, c_uint32]),
     "gl_dev_ipc_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), c_void_p]),
     "gl_dev_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "gl_dev_ipc_close": (c_int, [c_void_p, c_void_p]),

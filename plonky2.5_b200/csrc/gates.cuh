@@ -195,6 +195,25 @@ __global__ void __launch_bounds__(128) gate_quotient_kernel(const QuotientArgs a
     }
 }
 
+// tail of compute_quotient_polys: vals[i][k] = acc[k][bitrev(i)] / Z_H(g w_R^i), natural point order, row-major [R][pitch];
+// Z_H on the coset takes 2^rate_bits values: zh_inv[i mod 2^rate_bits] (plonky2 plonk/plonk_common.rs · ZeroPolyOnCoset::eval_inverse)
+__global__ void quotient_gather_kernel(const uint64_t* __restrict__ acc, uint64_t* __restrict__ out, uint32_t pitch, uint32_t n_ch, uint32_t bits,
+                                       uint32_t rate_bits, const uint64_t* __restrict__ zh_inv) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, R = 1ULL << bits;
+    if (i >= R) return;
+    const uint64_t src = gl::bitrev32((uint32_t)i, bits);
+    const uint64_t zi = zh_inv[i & ((1u << rate_bits) - 1)];
+    for (uint32_t k = 0; k < pitch; k++) out[i * pitch + k] = k < n_ch ? gl::mulc(acc[(uint64_t)k * R + src], zi) : 0;
+}
+// coefficients of the coset iFFT -> the quotient chunk polynomials: out[(k * n_chunks + c)][m] = coeffs[c * N + m][k] * shift^-(c N + m)
+__global__ void quotient_chunks_kernel(const uint64_t* __restrict__ coeffs, uint32_t pitch, uint32_t n_ch, uint32_t log_n, uint32_t rate_bits,
+                                       const uint64_t* __restrict__ shift_inv_pow, uint64_t* __restrict__ out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, R = 1ULL << (log_n + rate_bits), N = 1ULL << log_n;
+    if (j >= R) return;
+    const uint64_t c = j >> log_n, m = j & (N - 1), s = shift_inv_pow[j];
+    for (uint32_t k = 0; k < n_ch; k++) out[((uint64_t)k << rate_bits | c) * N + m] = gl::mulc(coeffs[j * pitch + k], s);
+}
+
 // Poseidon2Generator::run_once for a batch of rows: in[n][13] = 12 inputs + swap flag -> out[n][out_pitch] (135 wires)
 __global__ void poseidon2_witness_kernel(const uint64_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out, uint32_t out_pitch) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

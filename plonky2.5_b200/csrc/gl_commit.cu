@@ -203,6 +203,9 @@ struct gl_ctx {
     int ntt_version = 2;                  // GL_NTT_VERSION=1 selects the first-generation pass kernel (ntt.cuh) for A/B measurements
     int ntt_g10 = 8;                      // GL_NTT_G10=4: 4-column tiles for the 10-stage passes (smaller CTAs)
     cudaStream_t send_stream = nullptr;
+    cudaStream_t pull_stream = nullptr;   // peer -> local coefficient pulls of the coset-sharded plan.  NOT the copy stream: a stream that has
+                                          // carried peer copies keeps its copy-engine binding, and host->device chunks queued behind it then
+                                          // serialise with the send stream's shipments (measured: an 8 ms stall of the first shipment)
     cudaEvent_t ev_ntt[2] = {}, ev_sent[2] = {};
     bool sent_pending[2] = {false, false};
     DevBuf send_buf[2];
@@ -210,7 +213,7 @@ struct gl_ctx {
     bool trace = false;                    // GL_TRACE=1: per-coset timeline of the overlapped exchange on stderr (development aid)
     std::vector<cudaEvent_t> trace_ev;     // base, then per coset: ntt start, ntt end, send start, send end
     cudaEvent_t ev_sync = nullptr, ev_copyback = nullptr;
-    std::vector<cudaEvent_t> chunk_ev;
+    std::vector<cudaEvent_t> chunk_ev, pull_ev;
     cudaEvent_t ev[GL_N_STAGES + 1] = {};
     float stage_ms[GL_N_STAGES] = {};
     uint32_t launches[GL_N_STAGES] = {};
@@ -708,6 +711,7 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
         if ((ctx)->stream) cudaStreamSynchronize((ctx)->stream);           /* host buffers are only borrowed: nothing may */ \
         if ((ctx)->copy_stream) cudaStreamSynchronize((ctx)->copy_stream); /* read or write them after the call returns  */ \
         if ((ctx)->send_stream) cudaStreamSynchronize((ctx)->send_stream);                                      \
+        if ((ctx)->pull_stream) cudaStreamSynchronize((ctx)->pull_stream);                                      \
         return e.code;                           \
     }                                            \
     catch (const std::bad_alloc&) {              \
@@ -761,6 +765,7 @@ int gl_ctx_create(gl_ctx** out, int device) {
     for (int i = 0; i < 2; i++)
         if (cudaEventCreateWithFlags(&c->ev_ntt[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_sent[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (const char* m = getenv("GL_SCATTER_MODE")) c->scatter_mode = atoi(m);
     if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
     if (const char* m = getenv("GL_NTT_VERSION")) c->ntt_version = atoi(m);
@@ -790,10 +795,12 @@ void gl_ctx_destroy(gl_ctx* c) {
     DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->pull_ev) if (e) cudaEventDestroy(e);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->ev_copyback) cudaEventDestroy(c->ev_copyback);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->send_stream) { cudaStreamSynchronize(c->send_stream); cudaStreamDestroy(c->send_stream); }
+    if (c->pull_stream) { cudaStreamSynchronize(c->pull_stream); cudaStreamDestroy(c->pull_stream); }
     for (int i = 0; i < 2; i++) { if (c->ev_ntt[i]) cudaEventDestroy(c->ev_ntt[i]); if (c->ev_sent[i]) cudaEventDestroy(c->ev_sent[i]); }
     c->send_buf[0].release(); c->send_buf[1].release();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -933,6 +940,106 @@ int gl_lde_scatter(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint
     if (!cols) GL_THROW(GL_ERR_INVALID, "cols is NULL");
     return lde_scatter_impl(c, nullptr, cols, 0, n_cols, log_n, rate_bits, input_is_coeffs, peer_leaves, n_peers, leaf_pitch, col_off,
                             d_out_coeffs, coeff_pitch, first_coset);
+    GL_API_END(c)
+}
+
+// ---- coset-sharded commit: exchange coefficients, evaluate only the cosets this rank owns (include/gl_commit.h) ---------------------
+int gl_dev_intt(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, int input_is_coeffs,
+                uint64_t* d_out_coeffs, uint32_t coeff_pitch) {
+    GL_API_BEGIN(c)
+    check_shape(n_cols, log_n, 0, 0);
+    if (!d_cols || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL device pointer");
+    if (coeff_pitch % 4 || coeff_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "coeff_pitch must be a multiple of 4 and >= n_cols");
+    const int G = (round_up(n_cols, 8) - n_cols >= 4) ? 4 : 8;
+    if (coeff_pitch < round_up(n_cols, (uint32_t)G)) GL_THROW(GL_ERR_INVALID, "coeff_pitch too small for the padded column group");
+    const uint64_t N = 1ULL << log_n;
+    get_roots(c, log_n);
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+    record(c, GL_STAGE_TRANSPOSE);
+    dim3 tb(32, 8), tg((uint32_t)((N + 31) / 32), (coeff_pitch + 31) / 32);
+    if (input_is_coeffs) {
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, d_out_coeffs, coeff_pitch, coeff_pitch, n_cols, N);
+        CUDA_CHECK(cudaGetLastError());
+        c->launches[GL_STAGE_TRANSPOSE]++;
+        record(c, GL_STAGE_INTT);
+    } else {
+        c->vals.ensure(N * coeff_pitch);
+        ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(d_cols, col_stride, c->vals.p, coeff_pitch, coeff_pitch, n_cols, N);
+        CUDA_CHECK(cudaGetLastError());
+        c->launches[GL_STAGE_TRANSPOSE]++;
+        record(c, GL_STAGE_INTT);
+        run_ntt(c, c->vals.p, coeff_pitch, d_out_coeffs, coeff_pitch, round_up(n_cols, (uint32_t)G), log_n, true, nullptr, G, &c->launches[GL_STAGE_INTT]);
+    }
+    record(c, GL_STAGE_LDE);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT}) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_dev_lde_own_cosets(gl_ctx* c, uint64_t* const* peer_coeffs, uint64_t* const* d_stage, const uint32_t* pitches, const uint32_t* col_counts,
+                          const uint32_t* col_offsets, uint32_t n_peers, uint32_t self, uint32_t log_n, uint32_t rate_bits, uint64_t* d_leaves,
+                          uint32_t leaf_pitch) {
+    GL_API_BEGIN(c)
+    if (!peer_coeffs || !d_stage || !pitches || !col_counts || !col_offsets || !d_leaves) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_peers == 0 || (n_peers & (n_peers - 1)) || n_peers > (uint32_t)ntt::MAX_PEERS || self >= n_peers) GL_THROW(GL_ERR_INVALID, "bad peer count / rank");
+    if (n_peers > (1u << rate_bits)) GL_THROW(GL_ERR_INVALID, "coset sharding needs n_peers <= 2^rate_bits");
+    if (log_n + rate_bits > 31) GL_THROW(GL_ERR_UNSUPPORTED, "log_n + rate_bits > 31");
+    const uint64_t N = 1ULL << log_n;
+    const uint32_t blocks_per_rank = (1u << rate_bits) / n_peers, first_block = self * blocks_per_rank;
+    for (uint32_t q = 0; q < n_peers; q++) {
+        if (!peer_coeffs[q] || (q != self && !d_stage[q])) GL_THROW(GL_ERR_INVALID, "peer %u: NULL buffer", q);
+        if (pitches[q] % 4 || pitches[q] < col_counts[q] || col_offsets[q] % 4 || col_offsets[q] + col_counts[q] > leaf_pitch)
+            GL_THROW(GL_ERR_INVALID, "peer %u: bad column layout", q);
+    }
+    get_roots(c, log_n);
+    const auto& tabs = get_lde_tables(c, log_n, rate_bits);
+    if (c->pull_ev.size() < n_peers) {
+        size_t old = c->pull_ev.size();
+        c->pull_ev.resize(n_peers, nullptr);
+        for (size_t i = old; i < n_peers; i++) CUDA_CHECK(cudaEventCreateWithFlags(&c->pull_ev[i], cudaEventDisableTiming));
+    }
+    c->launches[GL_STAGE_LDE] = 0; c->stage_ms[GL_STAGE_LDE] = 0;
+    record(c, GL_STAGE_LDE);
+    // every pull is enqueued up front on the copy stream, nearest neighbour first (rank q pulls from q+1, q+2, ...: at any moment every
+    // rank reads from a different peer); the compute stream takes the blocks in the same order, own block first
+    CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->pull_stream, c->ev_sync, 0));        // staging buffers may still be read by an earlier call's NTTs
+    cudaEvent_t tr0 = nullptr, tr1 = nullptr;
+    uint64_t pulled_bytes = 0;
+    if (c->trace) { cudaEventCreate(&tr0); cudaEventCreate(&tr1); cudaEventRecord(tr0, c->pull_stream); }
+    for (uint32_t k = 1; k < n_peers; k++) pulled_bytes += N * pitches[(self + k) % n_peers] * 8;
+    for (uint32_t k = 1; k < n_peers; k++) {
+        const uint32_t q = (self + k) % n_peers;
+        CUDA_CHECK(cudaMemcpyAsync(d_stage[q], peer_coeffs[q], N * pitches[q] * 8, cudaMemcpyDefault, c->pull_stream));
+        CUDA_CHECK(cudaEventRecord(c->pull_ev[q], c->pull_stream));
+    }
+    if (c->trace) cudaEventRecord(tr1, c->pull_stream);
+    for (uint32_t k = 0; k < n_peers; k++) {
+        const uint32_t q = (self + k) % n_peers;
+        const uint64_t* coeffs = q == self ? peer_coeffs[q] : d_stage[q];
+        if (q != self) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->pull_ev[q], 0));
+        const int G = (round_up(col_counts[q], 8) - col_counts[q] >= 4 || pitches[q] % 8) ? 4 : 8;
+        if (pitches[q] < round_up(col_counts[q], (uint32_t)G)) GL_THROW(GL_ERR_INVALID, "peer %u: pitch too small for the padded column group", q);
+        for (uint32_t b = 0; b < blocks_per_rank; b++) {
+            const uint32_t s = h_bitrev(first_block + b, rate_bits);       // leaf block b of the batch is LDE coset bitrev_r(b)
+            uint64_t* dst = d_leaves + (uint64_t)b * N * leaf_pitch + col_offsets[q];
+            run_ntt(c, const_cast<uint64_t*>(coeffs), pitches[q], dst, leaf_pitch, round_up(col_counts[q], (uint32_t)G), log_n, false, &tabs[s], G,
+                    &c->launches[GL_STAGE_LDE]);
+        }
+    }
+    record(c, GL_STAGE_LEAF_HASH);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[GL_STAGE_LDE], c->ev[GL_STAGE_LDE], c->ev[GL_STAGE_LEAF_HASH]));
+    if (c->trace) {   // NVLink ingress of this rank: the G-1 coefficient blocks, back to back on the copy engine
+        cudaStreamSynchronize(c->pull_stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, tr0, tr1);
+        fprintf(stderr, "[gl trace dev %d] coset plan: pulled %.1f MB from %u peers in %.3f ms = %.1f GB/s (NVLink ingress); LDE stage %.3f ms\n", c->device,
+                pulled_bytes / 1e6, n_peers - 1, ms, ms > 0 ? pulled_bytes / ms / 1e6 : 0.0, c->stage_ms[GL_STAGE_LDE]);
+        cudaEventDestroy(tr0); cudaEventDestroy(tr1);
+    }
+    return GL_OK;
     GL_API_END(c)
 }
 
@@ -1763,6 +1870,42 @@ int gl_quotient_read(gl_ctx* c, gl_handle qh, uint64_t* out) {
     CUDA_CHECK(cudaMemcpyAsync(out, q->acc.p, q->n_rows * q->n_challenges * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_quotient_commit(gl_ctx* c, gl_handle qh, uint32_t cap_height, uint64_t* out_cap, gl_handle* out_batch) {
+    GL_API_BEGIN(c)
+    Quotient* q = find_quotient(c, qh);
+    Tree* t = find_tree(c, q->wires);
+    if (!out_cap) GL_THROW(GL_ERR_INVALID, "out_cap is NULL");
+    const uint32_t log_n = t->degree_log, r = t->rate_bits, bits = log_n + r, n_ch = q->n_challenges;
+    if (!t->has_coeffs) GL_THROW(GL_ERR_INVALID, "the wires batch is not a PolynomialBatch commit");
+    if (bits < 3) GL_THROW(GL_ERR_UNSUPPORTED, "quotient domain smaller than 8 points");
+    const uint64_t N = 1ULL << log_n, R = 1ULL << bits;
+    const uint32_t pitch = 4, n_chunks = 1u << r;
+    // Z_H(g w_R^i)^-1 for i mod 2^r, and shift^-j (host: 2^r inversions; the tables are filled on the device)
+    std::vector<uint64_t> zh(1u << r);
+    const uint64_t gN = gl::h_pow(gl::COSET_SHIFT, N), wr = gl::h_root_of_unity(r);
+    uint64_t cur = gN;
+    for (uint32_t j = 0; j < (1u << r); j++) { zh[j] = gl::h_inv(cur - 1); cur = gl::h_mul(cur, wr);   /* cur is a non-zero canonical element; Z_H != 0 on the coset */ }
+    DevBuf vals, coeffs, tab, cols;
+    vals.ensure(R * pitch); coeffs.ensure(R * pitch); tab.ensure(R + 8); cols.ensure((uint64_t)n_ch * R);
+    uint64_t* d_zh = tab.p + R;
+    CUDA_CHECK(cudaMemcpyAsync(d_zh, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    gates::quotient_gather_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, c->stream>>>(q->acc.p, vals.p, pitch, n_ch, bits, r, d_zh);
+    CUDA_CHECK(cudaGetLastError());
+    run_ntt(c, vals.p, pitch, coeffs.p, pitch, pitch, bits, true, nullptr, 4, nullptr);           // ifft: natural values -> natural coefficients
+    {
+        ntt::PowTable pt{};
+        uint64_t sq = gl::h_inv(gl::COSET_SHIFT);
+        for (uint32_t k = 0; k < 32; k++) { pt.g2k[k] = sq; sq = gl::h_mul(sq, sq); }
+        ntt::powers_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, c->stream>>>(tab.p, R, pt);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    gates::quotient_chunks_kernel<<<(uint32_t)((R + 255) / 256), 256, 0, c->stream>>>(coeffs.p, pitch, n_ch, log_n, r, tab.p, cols.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));   // zh is a host vector of this call
+    return commit_impl(c, nullptr, cols.p, N, n_ch * n_chunks, log_n, r, cap_height, 1, nullptr, nullptr, nullptr, out_cap, out_batch);
     GL_API_END(c)
 }
 

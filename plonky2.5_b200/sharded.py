@@ -96,11 +96,15 @@ class ShardedCommit:
     1-element all-reduce before hashing.  exchange="nccl": gl_dev_lde + all_to_all_single + gl_dev_repack (the baseline the
     fused path is measured against, and the collective fallback when peer mapping is unavailable)."""
 
-    def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch, exchange: str = "p2p"):
+    def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch, exchange: str = "auto"):
         self.ctx, self.plan, self.rank, self.dist, self.torch = ctx, plan, rank, dist, torch
         dev = torch.device("cuda", ctx.device)
         p = plan
         i64 = torch.int64
+        self._host_impl = None
+        self._auto = exchange == "auto"
+        if exchange == "auto":      # coset sharding whenever every rank can own whole cosets, else the column->row shipment
+            exchange = "coset" if p.world <= (1 << p.rate_bits) else "p2p"
         self.exchange = exchange
         self.coeffs = torch.empty((1 << p.log_n) * p.pitches[rank], dtype=i64, device=dev)  # [N][pitch_g]
         self.digests = torch.empty(max(p.digests_per_rank() * 4, 1), dtype=i64, device=dev)
@@ -119,6 +123,11 @@ class ShardedCommit:
         j = (rank * n_cosets // p.world) % n_cosets
         self._first_coset = int(format(j, "0%db" % p.rate_bits)[::-1], 2) if p.rate_bits else 0
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._coeff_ptr = None
+        if exchange == "coset" and p.world <= (1 << p.rate_bits) and self._init_coset(dev):
+            return
+        if exchange == "coset":
+            self.exchange = exchange = "p2p"
         if exchange == "p2p" and self._init_p2p(dev):
             return
         self.exchange = "nccl"      # requested, or the ranks cannot map each other's memory (all ranks agree on this)
@@ -127,11 +136,31 @@ class ShardedCommit:
         self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=i64, device=dev)    # [R/G][leaf_pitch]
         self.leaves_ptr = self.leaves.data_ptr()
 
+    def _init_coset(self, dev) -> bool:
+        """Coset-sharded plan (include/gl_commit.h · gl_dev_lde_own_cosets): export this rank's COEFFICIENT block, map every peer's, and
+        allocate local staging for the peers' blocks and the own leaf range.  Collective; False on every rank if any rank failed."""
+        p, torch = self.plan, self.torch
+        n = 1 << p.log_n
+        if not self._map_peers(dev, n * p.pitches[self.rank]):
+            return False
+        self._coeff_ptr, self._peer_coeffs = self.leaves_ptr, self._peer_ptrs     # the exported buffer holds coefficients in this mode
+        self._peer_ptrs = None
+        self._stage = [None if q == self.rank else torch.empty(n * p.pitches[q], dtype=torch.int64, device=dev) for q in range(p.world)]
+        self._stage_ptrs = (ctypes.c_void_p * p.world)(*[0 if t is None else t.data_ptr() for t in self._stage])
+        u32 = ctypes.c_uint32 * p.world
+        self._pitches, self._counts, self._offsets = u32(*p.pitches), u32(*p.col_counts), u32(*p.col_offsets)
+        self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=torch.int64, device=dev)
+        self.leaves_ptr = self.leaves.data_ptr()
+        return True
+
     def _init_p2p(self, dev) -> bool:
         """Export this rank's leaf buffer and map every peer's (CUDA IPC).  Collective; returns False on EVERY rank if any
         rank failed (no IPC in this container, no peer access), after releasing whatever was mapped."""
+        p = self.plan
+        return self._map_peers(dev, p.rows_per_rank * p.leaf_pitch)
+
+    def _map_peers(self, dev, words) -> bool:
         p, lib, h, torch, dist = self.plan, self.ctx.lib, self.ctx.handle, self.torch, self.dist
-        words = p.rows_per_rank * p.leaf_pitch
         own = ctypes.c_void_p()
         handle = (ctypes.c_uint8 * 64)()
         ok = lib.gl_dev_ipc_alloc(h, words, ctypes.byref(own), handle) == 0
@@ -168,15 +197,20 @@ class ShardedCommit:
         return True
 
     def close(self):
-        if self._peer_ptrs is not None:
+        if self._host_impl is not None:
+            self._host_impl.close()
+            self._host_impl = None
+        mapped = self._peer_ptrs if self._peer_ptrs is not None else getattr(self, "_peer_coeffs", None)
+        if mapped is not None:
             lib, h = self.ctx.lib, self.ctx.handle
+            own = self._coeff_ptr if self._coeff_ptr is not None else self.leaves_ptr
             self.dist.barrier()
-            for q, ptr in enumerate(self._peer_ptrs):
+            for q, ptr in enumerate(mapped):
                 if q != self.rank:
                     lib.gl_dev_ipc_close(h, ptr)
             self.dist.barrier()
-            lib.gl_dev_ipc_free(h, self.leaves_ptr)
-            self._peer_ptrs = None
+            lib.gl_dev_ipc_free(h, own)
+            self._peer_ptrs = self._peer_coeffs = None
 
     def _check(self, rc):
         if rc != 0:
@@ -189,6 +223,18 @@ class ShardedCommit:
         ncg = p.col_counts[self.rank]
         assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
         t0 = time.perf_counter()
+        if self.exchange == "coset":
+            # iNTT of the own column shard into the exported coefficient block; a stream-ordered 1-element all-reduce tells every rank
+            # that all blocks are complete; then pull + evaluate the own cosets of every block (pulls overlap the NTTs).  Nobody rewrites
+            # its block before all peers have pulled it: the next commit starts after the cap all-gather, which a rank enters only after
+            # its own hashing, i.e. after its pulls.
+            self._check(lib.gl_dev_intt(h, d_cols.data_ptr(), n, ncg, p.log_n, 0, self._coeff_ptr, p.pitches[self.rank]))
+            self._intt_ms = self.ctx.stage_times()[0]
+            with torch.cuda.stream(self._stream):
+                self.dist.all_reduce(self._flag)
+            self._check(lib.gl_dev_lde_own_cosets(h, self._peer_coeffs, self._stage_ptrs, self._pitches, self._counts, self._offsets, p.world,
+                                                  self.rank, p.log_n, p.rate_bits, self.leaves_ptr, p.leaf_pitch))
+            return self._hash()
         if self.exchange == "p2p":
             # Nobody may write into a leaf buffer its owner is still hashing: the previous commit ended with the cap
             # all-gather, which no rank enters before its own hashing is done, and every rank read its result — so all
@@ -229,6 +275,21 @@ class ShardedCommit:
         n = 1 << p.log_n
         ncg = p.col_counts[self.rank]
         assert tuple(h_cols.shape) == (ncg, n) and h_cols.is_contiguous() and not h_cols.is_cuda
+        if self.exchange == "coset" and self._auto:
+            # HOST columns: in the coset plan nothing can start before every rank's whole shard has crossed PCIe and gone through the
+            # iNTT, whereas the column->row plan hides the copy behind the LDE NTTs chunk by chunk (gl_lde_scatter) — so with
+            # exchange="auto" host inputs take that plan (its buffers are created on first use and kept)
+            if self._host_impl is None:
+                self._host_impl = ShardedCommit(self.ctx, self.plan, self.rank, self.dist, self.torch, exchange="p2p")
+            out = self._host_impl.commit_host(h_cols)
+            self.digests = self._host_impl.digests
+            return out
+        if self.exchange == "coset":
+            if getattr(self, "_h2d", None) is None:
+                self._h2d = torch.empty((ncg, n), dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
+            self._h2d.copy_(h_cols, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self.commit(self._h2d)
         if self.exchange != "p2p":
             d = h_cols.to(torch.device("cuda", self.ctx.device), non_blocking=True)
             torch.cuda.current_stream().synchronize()

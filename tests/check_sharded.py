@@ -48,8 +48,11 @@ def main():
         plan = ShardPlan(cols, log_n, r, h, world)
         c0, c1 = plan.col_range(rank)
         d = torch.from_numpy(x[c0:c1].view(np.int64).copy()).to(dev)
-        for mode in ("p2p", "nccl"):
+        for mode in ("coset", "p2p", "nccl"):
+            if mode == "coset" and world > (1 << r):
+                continue
             sc = ShardedCommit(ctx, plan, rank, dist, torch, exchange=mode)
+            assert sc.exchange == mode, (sc.exchange, mode)
             cap = sc.commit(d).reshape(-1, 4)
             cap2 = sc.commit_host(torch.from_numpy(x[c0:c1].view(np.int64).copy()).pin_memory()).reshape(-1, 4)   # host-column path; buffers reused
             dig = sc.digests.cpu().numpy().view(np.uint64)[:plan.digests_per_rank() * 4].reshape(-1, 4)

@@ -190,3 +190,55 @@ def test_partial_products_and_zs_match_oracle(ctx, log_n, n_routed, degree, n_ch
             den = (wires[j][n - 1] + betas[c] * sigmas[j][n - 1] + gammas[c]) % P
             acc = acc * num % P * pow(den, P - 2, P) % P
         assert acc == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n", [4, 8])
+def test_quotient_commit_tail(ctx, oc, log_n):
+    """gl_quotient_commit: acc / Z_H on the coset -> coset iFFT -> 2^r chunks of N coefficients -> from_coeffs commit.  Checked (a) against
+    the oracle's ifft + commit on the same accumulator values and (b) by the defining identity at sampled LDE points:
+    Z_H(x) * sum_c x^(cN) chunk_c(x) == acc(x)."""
+    import plonky25_b200 as g
+    lib, r, h, n_ch = ctx.lib, 3, 2, 2
+    n, R, bits = 1 << log_n, 1 << (log_n + 3), log_n + 3
+    wires = g.PolynomialBatch.from_values(list(splitmix_columns(90 + log_n, 135, n)), r, False, h, ctx=ctx)
+    alphas = np.array([11, 0xABCDEF0123456789 % P], dtype=np.uint64)
+    q = ctypes.c_uint64()
+    assert lib.gl_quotient_begin(ctx.handle, wires.merkle_tree._h, n_ch, ctypes.byref(q)) == 0
+    assert lib.gl_quotient_add_gate(ctx.handle, q.value, 0, 0, alphas.ctypes.data, 0, 0, 0) == 0
+    acc = np.zeros((n_ch, R), dtype=np.uint64)
+    assert lib.gl_quotient_read(ctx.handle, q.value, acc.ctypes.data) == 0
+    cap = np.zeros((1 << h, 4), dtype=np.uint64)
+    hb = ctypes.c_uint64()
+    rc = lib.gl_quotient_commit(ctx.handle, q.value, h, cap.ctypes.data, ctypes.byref(hb))
+    assert rc == 0, lib.gl_ctx_last_error(ctx.handle).decode()
+    lib.gl_quotient_end(ctx.handle, q.value)
+    batch = g.PolynomialBatch(ctx, g.MerkleTree(ctx, hb.value, cap.reshape(-1)), n_ch * 8)
+    chunks = batch.polynomials                                  # [16][N] coefficients
+    # (a) oracle: divide by Z_H, interpolate on the coset, split
+    rev = np.array([int(format(i, "0%db" % bits)[::-1], 2) for i in range(R)])
+    w_r = pow(1753635133440165772, 1 << (32 - 3), P)
+    zh_inv = [pow((pow(7, n, P) * pow(w_r, j, P) - 1) % P, P - 2, P) for j in range(8)]
+    inv7 = pow(7, P - 2, P)
+    want = []
+    for k in range(n_ch):
+        vals = [int(acc[k, rev[i]]) * zh_inv[i % 8] % P for i in range(R)]
+        co = [int(c) * pow(inv7, j, P) % P for j, c in enumerate(oc.ifft(np.array(vals, dtype=np.uint64)))]
+        want += [co[c * n:(c + 1) * n] for c in range(8)]
+    assert chunks.tolist() == want
+    ref = oc.commit(np.array(want, dtype=np.uint64), r, h, is_coeffs=True, want=())
+    assert np.array_equal(cap, ref["cap"])
+    # (b) identity at sampled points of the LDE coset
+    w_R = pow(1753635133440165772, 1 << (32 - bits), P)
+    for i in (0, 1, R // 3, R - 1):
+        x = 7 * pow(w_R, i, P) % P
+        zh = (pow(x, n, P) - 1) % P
+        for k in range(n_ch):
+            tot = 0
+            for c in reversed(range(8)):
+                ev = 0
+                for cf in reversed(chunks[k * 8 + c].tolist()):
+                    ev = (ev * x + cf) % P
+                tot = (tot * pow(x, n, P) + ev) % P
+            assert tot * zh % P == int(acc[k, rev[i]])
+    batch.merkle_tree.free(); wires.merkle_tree.free()
