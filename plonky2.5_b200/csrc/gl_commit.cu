@@ -131,10 +131,10 @@ inline uint32_t h_bitrev(uint32_t x, uint32_t bits) {
 }
 
 // how the log_n stages are split into shared-memory passes (each <= 10 stages, as even as possible)
-std::vector<uint32_t> plan_passes(uint32_t n) {
+std::vector<uint32_t> plan_passes(uint32_t n, uint32_t max_a = 10) {
     std::vector<uint32_t> v;
     if (n < 3) return v;
-    uint32_t k = (n + 9) / 10, base = n / k, rem = n % k;
+    uint32_t k = (n + max_a - 1) / max_a, base = n / k, rem = n % k;
     for (uint32_t i = 0; i < k; i++) v.push_back(base + (i < rem ? 1 : 0));
     return v;
 }
@@ -201,6 +201,9 @@ struct gl_ctx {
     //       stalls inside the NTT
     int scatter_mode = 3;
     int ntt_version = 2;                  // GL_NTT_VERSION=1 selects the first-generation pass kernel (ntt.cuh) for A/B measurements
+    int ntt_max_a = 10;                   // GL_NTT_MAX_A=11: 2048-row tiles, two passes instead of three at 2^21 / 2^22 — bit-exact and racecheck-clean,
+                                          // but measured SLOWER on B200 (2^22 x 256: iNTT 23.1 vs 19.8 ms, LDE 44.6 vs 37.5 ms): the 4-column tiles and
+                                          // 86 KB of shared memory cost more than the saved pass, so three (8,7,7) passes stay the default
     int ntt_g10 = 8;                      // GL_NTT_G10=4: 4-column tiles for the 10-stage passes (smaller CTAs)
     cudaStream_t send_stream = nullptr;
     cudaStream_t pull_stream = nullptr;   // peer -> local coefficient pulls of the coset-sharded plan.  NOT the copy stream: a stream that has
@@ -340,6 +343,10 @@ bool launch_pass2(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* 
         case 8: launch_pass2_a<G, 8>(c, p, (uint32_t)grid); break;
         case 9: launch_pass2_a<G, 9>(c, p, (uint32_t)grid); break;
         case 10: launch_pass2_a<G, 10>(c, p, (uint32_t)grid); break;
+        case 11:
+            if (G != 4) return false;                       // 2048-row tiles: 4 columns keep the tile at 68 KB
+            launch_pass2_a<4, 11>(c, p, (uint32_t)grid);
+            break;
         default: return false;
     }
     CUDA_CHECK(cudaGetLastError());
@@ -385,7 +392,10 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
              uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches, const ntt::Scatter* scatter = nullptr) {
     const uint64_t* W = get_roots(c, log_n);
     uint64_t n_inv = ifft ? gl::h_inv(((uint64_t)1 << log_n) % gl::P) : 1;
-    auto passes = plan_passes(log_n);
+    // the second-generation kernel has an 11-stage form (2048-row tiles of 4 columns): 2^21 and 2^22 then take two passes instead of three
+    const bool wide = c->ntt_version >= 2 && (G == 8 || G == 4) && c->ntt_max_a >= 11 && cols_padded % 4 == 0 &&
+                      (log_n + 9) / 10 > (log_n + 10) / 11 && src_pitch % 2 == 0 && dst_pitch % 2 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
+    auto passes = plan_passes(log_n, wide ? 11 : 10);
     if (passes.empty()) {
         dim3 grid((cols_padded + 63) / 64, 1u << log_n);
         ntt::ntt_tiny_kernel<<<grid, 64, 0, c->stream>>>(src, dst, src_pitch, dst_pitch, cols_padded, log_n,
@@ -425,6 +435,7 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
             // 128-bit accesses need even pitches and 16-byte aligned bases (true for every buffer this library lays out)
             const bool aligned = p.src_pitch % 2 == 0 && p.dst_pitch % 2 == 0 && ((uintptr_t)p.src % 16 == 0) && ((uintptr_t)p.dst % 16 == 0);
             if (g == 8 && p.a == 10 && c->ntt_g10 == 4) g = 4;
+            if (p.a == 11) g = 4;
             if (aligned && (g == 8 ? launch_pass2<8>(c, p, cols_padded, launches) : launch_pass2<4>(c, p, cols_padded, launches))) {
                 log_blk -= passes[i];
                 continue;
@@ -770,6 +781,7 @@ int gl_ctx_create(gl_ctx** out, int device) {
     if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
     if (const char* m = getenv("GL_NTT_VERSION")) c->ntt_version = atoi(m);
     if (const char* m = getenv("GL_NTT_G10")) c->ntt_g10 = atoi(m);
+    if (const char* m = getenv("GL_NTT_MAX_A")) c->ntt_max_a = atoi(m);
     if (cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&c->ev_copyback, cudaEventDisableTiming) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     for (auto& e : c->ev)
