@@ -149,6 +149,31 @@ __device__ __forceinline__ void dft16_cs(uint64_t (&x)[16]) {
     for (int j = 0; j < 8; j++) { x[j] = lo8[j]; x[j + 8] = hi8[j]; }
 }
 
+// ---- TMA bulk copy (cp.async.bulk, the non-tensor form) + mbarrier: the round-twiddle table of a pass is one contiguous block in
+// global memory, so a single elected thread hands the whole copy to the TMA unit and every thread later waits on the mbarrier's phase.
+// (The TILE itself is not moved by TMA: its rows are 2^b_lo rows apart, the first round consumes the loads straight from registers,
+// and the pass is bound by the integer ALU pipe — ncu: alu 75-80 %, math-pipe throttle 3.6-3.9 warps per issue vs long scoreboard
+// 0.5-1.8, DRAM 21-26 % — so staging the tile through shared memory would add LDS instructions without hiding anything)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+}
+
 // ---- pass structure ------------------------------------------------------------------------------------------------------------------------
 // rounds of a 2^A-point pass: non-final rounds are radix-8 (radix-16 for A = 8) followed by a table twiddle; the final round is the
 // all-shift radix-16 where the stage count allows it
@@ -212,7 +237,8 @@ __global__ void __launch_bounds__((1 << A) * G / 16 >= 32 ? (1 << A) * G / 16 : 
 ntt_pass_kernel(const ntt::PassParams p) {
     constexpr int NR = plan_n(A);
     constexpr uint32_t T = 1u << A, G2 = G / 2, PAD = pad_shift<A>();
-    extern __shared__ __align__(16) uint64_t sm2[];
+    extern __shared__ __align__(128) uint64_t sm2[];
+    __shared__ uint64_t wl_bar;                               // mbarrier of the twiddle-table bulk copy
     uint64_t* tile = sm2;                                     // [T + T/2^PAD][G]
     uint64_t* Wl = sm2 + (size_t)(T + (T >> PAD)) * G;        // w_T^j, j < T
     const uint32_t tid = threadIdx.x;
@@ -226,6 +252,10 @@ ntt_pass_kernel(const ntt::PassParams p) {
     const uint32_t q8 = tid / G2, c2 = tid % G2, q16 = tid / G, c1 = tid % G;
     const uint32_t col2 = cg * G + 2 * c2, col1 = cg * G + c1;
 
+    if (NR > 1) {
+        if (tid == 0) mbar_init(&wl_bar, 1);
+        __syncthreads();                                      // the initialised barrier is visible to every waiter
+    }
     ulonglong2 v[8];     // radix-8 view: v[e] = columns (col2, col2 + 1) of tile row insk(q8, sh, e, 3)
     uint64_t u[16];      // radix-16 view: u[e] = column col1 of tile row insk(q16, sh, e, 4)
     constexpr int K0 = plan_k(A, 0);
@@ -245,8 +275,8 @@ ntt_pass_kernel(const ntt::PassParams p) {
             }
         }
     }
-    if (NR > 1)
-        for (uint32_t e = tid; e < T; e += blockDim.x) Wl[e] = __ldg(p.Wa + e);
+    // (the tile's own loads were issued above; the table copy now runs on the TMA unit in their shadow)
+    if (NR > 1 && tid == 0) tma_bulk_g2s(Wl, p.Wa, T * 8, &wl_bar);
     if (p.pre != nullptr) {
         if (K0 == 3) {
 #pragma unroll
@@ -264,7 +294,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
             }
         }
     }
-    if (NR > 1) __syncthreads();   // Wl ready
+    if (NR > 1) mbar_wait(&wl_bar, 0);   // Wl has landed (phase 0 of the mbarrier completes when all T*8 bytes have arrived)
 
     int done = 0;
 #pragma unroll
