@@ -159,10 +159,17 @@ int gl_fri_read(gl_ctx* ctx, gl_handle fri, uint64_t* out_coeffs_ext, uint64_t* 
  *   GL_GATE_POSEIDON2       /root/reference/src/common/poseidon2/poseidon2_gate.rs:233-310   135 wires, 123 constraints (param unused)
  *   GL_GATE_U32_ARITHMETIC  /root/reference/src/common/u32/gates/arithmetic_u32.rs:103-166    param = num_ops (3 at 135 wires / 80 routed):
  *                                                                                             38*num_ops wires, 36*num_ops constraints
+ *   GL_GATE_U32_ADD_MANY    .../add_many_u32.rs:103-143        param = num_addends | num_ops << 8      (num_addends+21)*num_ops wires, 21*num_ops constraints
+ *   GL_GATE_U32_SUBTRACTION .../subtraction_u32.rs:100-134     param = num_ops (<= 6)                   21*num_ops wires, 19*num_ops constraints
+ *   GL_GATE_U32_RANGE_CHECK .../range_check_u32.rs:70-92       param = num_input_limbs (<= 7)           17*n wires, 17*n constraints
+ *   GL_GATE_U32_INTERLEAVE  .../interleave_u32.rs:104-140      param = num_ops (<= 3)                   34*num_ops wires and constraints
+ *   GL_GATE_UNINTERLEAVE_TO_U32 / _TO_B32  .../uninterleave_to_u32.rs:91-134, uninterleave_to_b32.rs:115-168   param = num_ops (<= 2)   67*num_ops each
+ *   GL_GATE_COMPARISON      .../comparison.rs:112-190          param = num_bits | num_chunks << 8      5*num_chunks + chunk_bits + 5 wires, + 6 constraints
  * gl_quotient_add_gate:  acc[k][row] += filter(row) * sum_i alphas[k]^(constraint_offset + i) * constraint_i(wires(row)),  k < n_challenges
  * (alphas are BASE-field challenges, as upstream; filter(row) = column filter_col of the batch filter_batch at the same row — the LDE of the
  * gate's selector filter — or 1 when filter_batch == 0).  gl_quotient_read: [n_challenges][R] words, row order = the leaves' (bit-reversed). */
-enum { GL_GATE_POSEIDON2 = 0, GL_GATE_U32_ARITHMETIC = 1 };
+enum { GL_GATE_POSEIDON2 = 0, GL_GATE_U32_ARITHMETIC = 1, GL_GATE_U32_ADD_MANY = 2, GL_GATE_U32_SUBTRACTION = 3, GL_GATE_U32_RANGE_CHECK = 4,
+       GL_GATE_U32_INTERLEAVE = 5, GL_GATE_UNINTERLEAVE_TO_U32 = 6, GL_GATE_UNINTERLEAVE_TO_B32 = 7, GL_GATE_COMPARISON = 8 };
 int gl_gate_num_wires(int kind, uint32_t param);
 int gl_gate_num_constraints(int kind, uint32_t param);
 /* every constraint value of every row, uncombined (host rows [n_rows][num_wires] -> out [n_rows][num_constraints]); tests, debugging */

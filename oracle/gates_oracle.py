@@ -277,3 +277,227 @@ def partial_products_and_zs(wires, sigmas, k_is, betas, gammas, degree, log_n):
         zs.append(z_col)
         pps.extend(pp_cols)
     return zs + pps
+
+
+# ---- the reference's other u32 / b32 gates (all under /root/reference/src/common/u32/gates/) ----------------------------------------
+# Each *_eval follows the gate's eval_unfiltered line by line (the packed base evaluators compute the same values); each *_witness fills a
+# valid row the way the gate's generator does, for tests.  plonky2's reduce_with_powers(terms, a) = sum_i terms[i] * a^i.
+def _range_product(v, n):
+    prod = 1
+    for x in range(n):
+        prod = prod * (v - x) % P
+    return prod
+
+
+def _rwp(terms, alpha):
+    acc = 0
+    for t in reversed(list(terms)):
+        acc = (acc * alpha + t) % P
+    return acc
+
+
+def add_many_num_ops(num_addends, num_wires=135, num_routed=80):
+    """add_many_u32.rs:52-57"""
+    return min(num_wires // (num_addends + 3 + 18), num_routed // (num_addends + 3))
+
+
+def add_many_eval(w, num_addends, num_ops):
+    """add_many_u32.rs:103-143 (result limbs: 16 x 2 bits, carry limbs: 2 x 2 bits)"""
+    w = [int(x) % P for x in w]
+    c, stride = [], num_addends + 3
+    for i in range(num_ops):
+        addends = w[stride * i:stride * i + num_addends]
+        carry, out_res, out_carry = w[stride * i + num_addends], w[stride * i + num_addends + 1], w[stride * i + num_addends + 2]
+        computed = (sum(addends) + carry) % P
+        c.append((out_carry * (1 << 32) + out_res - computed) % P)
+        res_l = car_l = 0
+        for j in reversed(range(18)):
+            limb = w[stride * num_ops + 18 * i + j]
+            c.append(_range_product(limb, 4))
+            if j < 16:
+                res_l = (4 * res_l + limb) % P
+            else:
+                car_l = (4 * car_l + limb) % P
+        c.append((res_l - out_res) % P)
+        c.append((car_l - out_carry) % P)
+    return c
+
+
+def add_many_witness(ops, num_addends, num_wires=135):
+    """ops: per op (addends[num_addends] u32, carry u32)"""
+    num_ops, stride = len(ops), num_addends + 3
+    w = [0] * num_wires
+    for i, (addends, carry) in enumerate(ops):
+        out = sum(addends) + carry
+        res, car = out & 0xFFFFFFFF, out >> 32
+        w[stride * i:stride * i + num_addends] = list(addends)
+        w[stride * i + num_addends:stride * i + num_addends + 3] = [carry, res, car]
+        for j in range(18):
+            w[stride * num_ops + 18 * i + j] = ((res >> (2 * j)) & 3) if j < 16 else ((car >> (2 * (j - 16))) & 3)
+    return w
+
+
+def subtraction_eval(w, num_ops):
+    """subtraction_u32.rs:100-134"""
+    w = [int(x) % P for x in w]
+    c = []
+    for i in range(num_ops):
+        x, y, borrow, out_res, out_borrow = w[5 * i:5 * i + 5]
+        initial = (x - y - borrow) % P
+        c.append((out_res - (initial + (1 << 32) * out_borrow)) % P)
+        comb = 0
+        for j in reversed(range(16)):
+            limb = w[5 * num_ops + 16 * i + j]
+            c.append(_range_product(limb, 4))
+            comb = (4 * comb + limb) % P
+        c.append((comb - out_res) % P)
+        c.append(out_borrow * (1 - out_borrow) % P)
+    return c
+
+
+def subtraction_witness(ops, num_wires=135):
+    num_ops = len(ops)
+    w = [0] * num_wires
+    for i, (x, y, b) in enumerate(ops):
+        d = x - y - b
+        res, bo = (d, 0) if d >= 0 else (d + (1 << 32), 1)
+        w[5 * i:5 * i + 5] = [x, y, b, res, bo]
+        for j in range(16):
+            w[5 * num_ops + 16 * i + j] = (res >> (2 * j)) & 3
+    return w
+
+
+def range_check_eval(w, num_input_limbs):
+    """range_check_u32.rs:70-92"""
+    w = [int(x) % P for x in w]
+    c = []
+    for i in range(num_input_limbs):
+        aux = w[num_input_limbs + 16 * i:num_input_limbs + 16 * i + 16]
+        c.append((_rwp(aux, 4) - w[i]) % P)
+        for a in aux:
+            c.append(_range_product(a, 4))
+    return c
+
+
+def range_check_witness(limbs, num_wires=135):
+    n = len(limbs)
+    w = [0] * num_wires
+    for i, v in enumerate(limbs):
+        w[i] = v
+        for j in range(16):
+            w[n + 16 * i + j] = (v >> (2 * j)) & 3
+    return w
+
+
+def interleave_eval(w, num_ops):
+    """interleave_u32.rs:104-140: bits are big-endian"""
+    w = [int(x) % P for x in w]
+    c = []
+    for i in range(num_ops):
+        x, x_int = w[2 * i], w[2 * i + 1]
+        bits = w[2 * num_ops + 32 * i:2 * num_ops + 32 * (i + 1)]
+        c.append((_rwp(reversed(bits), 2) - x) % P)
+        c.append((_rwp(reversed(bits), 4) - x_int) % P)
+        for b in bits:
+            c.append(_range_product(b, 2))
+    return c
+
+
+def interleave_witness(xs, num_wires=135):
+    num_ops = len(xs)
+    w = [0] * num_wires
+    for i, x in enumerate(xs):
+        bits = [(x >> (31 - k)) & 1 for k in range(32)]
+        w[2 * i] = x
+        w[2 * i + 1] = sum(b << (2 * (31 - k)) for k, b in enumerate(bits))
+        w[2 * num_ops + 32 * i:2 * num_ops + 32 * (i + 1)] = bits
+    return w
+
+
+def uninterleave_eval(w, num_ops, to_b32):
+    """uninterleave_to_u32.rs:91-134 (to_b32=False) / uninterleave_to_b32.rs:115-168 (True)"""
+    w = [int(x) % P for x in w]
+    c = []
+    for i in range(num_ops):
+        x_int, evens, odds = w[3 * i:3 * i + 3]
+        bits = w[3 * num_ops + 64 * i:3 * num_ops + 64 * (i + 1)]
+        c.append((_rwp(reversed(bits), 2) - x_int) % P)
+        ce = co = 0
+        for j in range(32):
+            coeff = (1 << (2 * (32 - j - 1))) if to_b32 else (1 << (32 - j - 1))
+            ce = (ce + coeff * bits[2 * j]) % P
+            co = (co + coeff * bits[2 * j + 1]) % P
+        c.append((ce - evens) % P)
+        c.append((co - odds) % P)
+        for b in bits:
+            c.append(_range_product(b, 2))
+    return c
+
+
+def uninterleave_witness(xs, to_b32, num_wires=135):
+    num_ops = len(xs)
+    w = [0] * num_wires
+    for i, x in enumerate(xs):
+        bits = [(x >> (63 - k)) & 1 for k in range(64)]
+        ce = co = 0
+        for j in range(32):
+            coeff = (1 << (2 * (32 - j - 1))) if to_b32 else (1 << (32 - j - 1))
+            ce += coeff * bits[2 * j]
+            co += coeff * bits[2 * j + 1]
+        w[3 * i:3 * i + 3] = [x, ce, co]
+        w[3 * num_ops + 64 * i:3 * num_ops + 64 * (i + 1)] = bits
+    return w
+
+
+def comparison_eval(w, num_bits, num_chunks):
+    """comparison.rs:112-190 (ComparisonGate::eval_unfiltered)"""
+    w = [int(x) % P for x in w]
+    chunk_bits = -(-num_bits // num_chunks)
+    c = []
+    first_input, second_input = w[0], w[1]
+    fc = w[4:4 + num_chunks]
+    sc = w[4 + num_chunks:4 + 2 * num_chunks]
+    c.append((_rwp(fc, 1 << chunk_bits) - first_input) % P)
+    c.append((_rwp(sc, 1 << chunk_bits) - second_input) % P)
+    msd = 0
+    for i in range(num_chunks):
+        c.append(_range_product(fc[i], 1 << chunk_bits))
+        c.append(_range_product(sc[i], 1 << chunk_bits))
+        diff = (sc[i] - fc[i]) % P
+        eq_dummy, chunks_equal = w[4 + 2 * num_chunks + i], w[4 + 3 * num_chunks + i]
+        c.append((diff * eq_dummy - (1 - chunks_equal)) % P)
+        c.append(chunks_equal * diff % P)
+        inter = w[4 + 4 * num_chunks + i]
+        c.append((inter - chunks_equal * msd) % P)
+        msd = (inter + (1 - chunks_equal) * diff) % P
+    c.append((w[3] - msd) % P)
+    bits = w[4 + 5 * num_chunks:4 + 5 * num_chunks + chunk_bits + 1]
+    for b in bits:
+        c.append(b * (1 - b) % P)
+    c.append(((1 << chunk_bits) + w[3] - _rwp(bits, 2)) % P)
+    c.append((w[2] - bits[chunk_bits]) % P)
+    return c
+
+
+def comparison_witness(a, b, num_bits, num_chunks, num_wires=135):
+    """ComparisonGenerator::run_once: result = (a <= b)"""
+    chunk_bits = -(-num_bits // num_chunks)
+    w = [0] * num_wires
+    w[0], w[1] = a, b
+    fc = [(a >> (chunk_bits * i)) & ((1 << chunk_bits) - 1) for i in range(num_chunks)]
+    sc = [(b >> (chunk_bits * i)) & ((1 << chunk_bits) - 1) for i in range(num_chunks)]
+    msd = 0
+    for i in range(num_chunks):
+        diff = (sc[i] - fc[i]) % P
+        eq = 1 if diff == 0 else 0
+        w[4 + i], w[4 + num_chunks + i] = fc[i], sc[i]
+        w[4 + 2 * num_chunks + i] = pow(diff, P - 2, P) if diff else 1        # equality_dummy: 1/diff, or 1 when the chunks are equal
+        w[4 + 3 * num_chunks + i] = eq
+        w[4 + 4 * num_chunks + i] = eq * msd % P
+        msd = (w[4 + 4 * num_chunks + i] + (1 - eq) * diff) % P
+    w[3] = msd
+    v = ((1 << chunk_bits) + msd) % P
+    for k in range(chunk_bits + 1):
+        w[4 + 5 * num_chunks + k] = (v >> k) & 1
+    w[2] = w[4 + 5 * num_chunks + chunk_bits]
+    return w

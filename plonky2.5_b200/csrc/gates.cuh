@@ -20,7 +20,7 @@ constexpr int P2_WIRE_SWAP = 24, P2_START_DELTA = 25, P2_START_RF_BEGIN = 29, P2
 constexpr int P2_NUM_WIRES = P2_START_RF_END + 12 * 4;                 // 135
 constexpr int P2_NUM_CONSTRAINTS = 12 * 7 + 22 + 12 + 1 + 4;           // 123
 constexpr int U32_LIMBS = 32, U32_ROUTED = 6;
-constexpr int MAX_CONSTRAINTS = 128, MAX_CHALLENGES = 4;
+constexpr int MAX_CONSTRAINTS = 160, MAX_CHALLENGES = 4;
 
 __device__ __forceinline__ uint64_t dbl(uint64_t x) { return gl::add(x, x); }
 
@@ -138,12 +138,150 @@ __device__ __forceinline__ void u32_arithmetic_gate(Wires&& w, Emit&& emit, uint
     }
 }
 
-enum { GATE_POSEIDON2 = 0, GATE_U32_ARITHMETIC = 1 };
+// ---- the reference's other u32 / b32 gates (/root/reference/src/common/u32/gates/*.rs · eval_unfiltered, same constraint order) -------
+__device__ __forceinline__ uint64_t range4(uint64_t v) {   // v (v-1) (v-2) (v-3)
+    return gl::mulc(gl::mulc(gl::mulc(v, gl::sub(v, 1)), gl::sub(v, 2)), gl::sub(v, 3));
+}
+__device__ __forceinline__ uint64_t range2(uint64_t v) { return gl::mulc(v, gl::sub(v, 1)); }
+__device__ __forceinline__ uint64_t times4(uint64_t v) { return dbl(dbl(v)); }
+
+// add_many_u32.rs:103-143; param = num_addends | num_ops << 8; 16 result limbs + 2 carry limbs of 2 bits
+template <class Wires, class Emit>
+__device__ __forceinline__ void add_many_gate(Wires&& w, Emit&& emit, uint32_t param) {
+    const uint32_t na = param & 0xFF, num_ops = param >> 8, stride = na + 3;
+    for (uint32_t i = 0; i < num_ops; i++) {
+        uint64_t sum = w(stride * i + na);                                    // carry
+        for (uint32_t j = 0; j < na; j++) sum = gl::add(sum, w(stride * i + j));
+        const uint64_t res = w(stride * i + na + 1), car = w(stride * i + na + 2);
+        emit(gl::sub(gl::add(gl::mulc(car, 1ULL << 32), res), sum));
+        uint64_t rl = 0, cl = 0;
+#pragma unroll 1
+        for (int j = 17; j >= 0; j--) {
+            const uint64_t limb = w(stride * num_ops + 18 * i + j);
+            emit(range4(limb));
+            if (j < 16) rl = gl::add(times4(rl), limb);
+            else cl = gl::add(times4(cl), limb);
+        }
+        emit(gl::sub(rl, res));
+        emit(gl::sub(cl, car));
+    }
+}
+// subtraction_u32.rs:100-134; param = num_ops
+template <class Wires, class Emit>
+__device__ __forceinline__ void subtraction_gate(Wires&& w, Emit&& emit, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint64_t x = w(5 * i), y = w(5 * i + 1), b = w(5 * i + 2), res = w(5 * i + 3), bo = w(5 * i + 4);
+        const uint64_t initial = gl::sub(gl::sub(x, y), b);
+        emit(gl::sub(res, gl::add(initial, gl::mulc(bo, 1ULL << 32))));
+        uint64_t comb = 0;
+#pragma unroll 1
+        for (int j = 15; j >= 0; j--) {
+            const uint64_t limb = w(5 * num_ops + 16 * i + j);
+            emit(range4(limb));
+            comb = gl::add(times4(comb), limb);
+        }
+        emit(gl::sub(comb, res));
+        emit(gl::mulc(bo, gl::sub(1, bo)));
+    }
+}
+// range_check_u32.rs:70-92; param = num_input_limbs
+template <class Wires, class Emit>
+__device__ __forceinline__ void range_check_gate(Wires&& w, Emit&& emit, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t sum = 0;
+        for (int j = 15; j >= 0; j--) sum = gl::add(times4(sum), w(n + 16 * i + j));   // reduce_with_powers(aux, 4)
+        emit(gl::sub(sum, w(i)));
+#pragma unroll 1
+        for (int j = 0; j < 16; j++) emit(range4(w(n + 16 * i + j)));
+    }
+}
+// interleave_u32.rs:104-140; param = num_ops; 32 big-endian bits per op
+template <class Wires, class Emit>
+__device__ __forceinline__ void interleave_gate(Wires&& w, Emit&& emit, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint32_t b0 = 2 * num_ops + 32 * i;
+        uint64_t v2 = 0, v4 = 0;
+        for (int k = 0; k < 32; k++) {                                        // bits[0] is the most significant
+            const uint64_t bit = w(b0 + k);
+            v2 = gl::add(dbl(v2), bit);
+            v4 = gl::add(times4(v4), bit);
+        }
+        emit(gl::sub(v2, w(2 * i)));
+        emit(gl::sub(v4, w(2 * i + 1)));
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) emit(range2(w(b0 + k)));
+    }
+}
+// uninterleave_to_u32.rs:91-134 (B32 = false) / uninterleave_to_b32.rs:115-168 (B32 = true); param = num_ops; 64 big-endian bits per op
+template <bool B32, class Wires, class Emit>
+__device__ __forceinline__ void uninterleave_gate(Wires&& w, Emit&& emit, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint32_t b0 = 3 * num_ops + 64 * i;
+        uint64_t v2 = 0, ce = 0, co = 0;
+        for (int k = 0; k < 64; k++) v2 = gl::add(dbl(v2), w(b0 + k));
+        for (int j = 0; j < 32; j++) {                                        // Horner over j: coefficient 2^(31-j) or 4^(31-j)
+            ce = gl::add(B32 ? times4(ce) : dbl(ce), w(b0 + 2 * j));
+            co = gl::add(B32 ? times4(co) : dbl(co), w(b0 + 2 * j + 1));
+        }
+        emit(gl::sub(v2, w(3 * i)));
+        emit(gl::sub(ce, w(3 * i + 1)));
+        emit(gl::sub(co, w(3 * i + 2)));
+#pragma unroll 1
+        for (int k = 0; k < 64; k++) emit(range2(w(b0 + k)));
+    }
+}
+// comparison.rs:112-190; param = num_bits | num_chunks << 8
+template <class Wires, class Emit>
+__device__ __forceinline__ void comparison_gate(Wires&& w, Emit&& emit, uint32_t param) {
+    const uint32_t num_bits = param & 0xFF, nc = param >> 8, chunk_bits = (num_bits + nc - 1) / nc;
+    const uint64_t base = 1ULL << chunk_bits;
+    uint64_t f = 0, s = 0;
+    for (int i = (int)nc - 1; i >= 0; i--) {
+        f = gl::add(gl::mulc(f, base), w(4 + i));
+        s = gl::add(gl::mulc(s, base), w(4 + nc + i));
+    }
+    emit(gl::sub(f, w(0)));
+    emit(gl::sub(s, w(1)));
+    uint64_t msd = 0;
+    for (uint32_t i = 0; i < nc; i++) {
+        const uint64_t fc = w(4 + i), sc = w(4 + nc + i);
+        uint64_t pf = 1, ps = 1;
+        for (uint64_t x = 0; x < base; x++) { pf = gl::mulc(pf, gl::sub(fc, x)); ps = gl::mulc(ps, gl::sub(sc, x)); }
+        emit(pf);
+        emit(ps);
+        const uint64_t diff = gl::sub(sc, fc), dummy = w(4 + 2 * nc + i), eq = w(4 + 3 * nc + i), inter = w(4 + 4 * nc + i);
+        emit(gl::sub(gl::mulc(diff, dummy), gl::sub(1, eq)));
+        emit(gl::mulc(eq, diff));
+        emit(gl::sub(inter, gl::mulc(eq, msd)));
+        msd = gl::add(inter, gl::mulc(gl::sub(1, eq), diff));
+    }
+    emit(gl::sub(w(3), msd));
+    uint64_t comb = 0;
+    for (uint32_t k = 0; k <= chunk_bits; k++) {
+        const uint64_t bit = w(4 + 5 * nc + k);
+        emit(gl::mulc(bit, gl::sub(1, bit)));
+    }
+    for (int k = (int)chunk_bits; k >= 0; k--) comb = gl::add(dbl(comb), w(4 + 5 * nc + k));
+    emit(gl::sub(gl::add(base, w(3)), comb));
+    emit(gl::sub(w(2), w(4 + 5 * nc + chunk_bits)));
+}
+
+enum { GATE_POSEIDON2 = 0, GATE_U32_ARITHMETIC = 1, GATE_U32_ADD_MANY = 2, GATE_U32_SUBTRACTION = 3, GATE_U32_RANGE_CHECK = 4,
+       GATE_U32_INTERLEAVE = 5, GATE_UNINTERLEAVE_TO_U32 = 6, GATE_UNINTERLEAVE_TO_B32 = 7, GATE_COMPARISON = 8 };
 
 template <class Wires, class Emit>
 __device__ __forceinline__ void eval_gate(int kind, uint32_t param, Wires&& w, Emit&& emit) {
-    if (kind == GATE_POSEIDON2) poseidon2_gate(w, emit);
-    else u32_arithmetic_gate(w, emit, param);
+    switch (kind) {
+        case GATE_POSEIDON2: poseidon2_gate(w, emit); break;
+        case GATE_U32_ARITHMETIC: u32_arithmetic_gate(w, emit, param); break;
+        case GATE_U32_ADD_MANY: add_many_gate(w, emit, param); break;
+        case GATE_U32_SUBTRACTION: subtraction_gate(w, emit, param); break;
+        case GATE_U32_RANGE_CHECK: range_check_gate(w, emit, param); break;
+        case GATE_U32_INTERLEAVE: interleave_gate(w, emit, param); break;
+        case GATE_UNINTERLEAVE_TO_U32: uninterleave_gate<false>(w, emit, param); break;
+        case GATE_UNINTERLEAVE_TO_B32: uninterleave_gate<true>(w, emit, param); break;
+        default: comparison_gate(w, emit, param); break;
+    }
 }
 
 // every constraint of every row, uncombined (tests): out[row][i]

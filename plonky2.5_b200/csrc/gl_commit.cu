@@ -1771,19 +1771,44 @@ int gl_fri_read(gl_ctx* c, gl_handle fh, uint64_t* out_coeffs, uint64_t* out_val
 
 // ------------------------------------------------------------------------------------------------ gates / quotient (§8f ranks 3-4)
 namespace {
+// wires / constraints per gate kind (param as documented in include/gl_commit.h); -1 for a bad kind or parameter
 int gate_wires(int kind, uint32_t param) {
-    if (kind == GL_GATE_POSEIDON2) return gates::P2_NUM_WIRES;
-    if (kind == GL_GATE_U32_ARITHMETIC) return (int)((gates::U32_ROUTED + gates::U32_LIMBS) * param);
-    return -1;
+    const uint32_t lo = param & 0xFF, hi = param >> 8;
+    switch (kind) {
+        case GL_GATE_POSEIDON2: return gates::P2_NUM_WIRES;
+        case GL_GATE_U32_ARITHMETIC: return param >= 1 && param <= 3 ? (int)((gates::U32_ROUTED + gates::U32_LIMBS) * param) : -1;
+        case GL_GATE_U32_ADD_MANY: return lo >= 1 && lo <= 24 && hi >= 1 && (lo + 3 + 18) * hi <= 135 ? (int)((lo + 3 + 18) * hi) : -1;
+        case GL_GATE_U32_SUBTRACTION: return param >= 1 && param <= 6 ? (int)(21 * param) : -1;
+        case GL_GATE_U32_RANGE_CHECK: return param >= 1 && param <= 7 ? (int)(17 * param) : -1;
+        case GL_GATE_U32_INTERLEAVE: return param >= 1 && param <= 3 ? (int)(34 * param) : -1;
+        case GL_GATE_UNINTERLEAVE_TO_U32:
+        case GL_GATE_UNINTERLEAVE_TO_B32: return param >= 1 && param <= 2 ? (int)(67 * param) : -1;
+        case GL_GATE_COMPARISON: {
+            if (lo < 1 || lo > 63 || hi < 1 || hi > lo) return -1;
+            const uint32_t cb = (lo + hi - 1) / hi;
+            return cb <= 6 && 4 + 5 * hi + cb + 1 <= 135 ? (int)(4 + 5 * hi + cb + 1) : -1;
+        }
+        default: return -1;
+    }
 }
 int gate_constraints(int kind, uint32_t param) {
-    if (kind == GL_GATE_POSEIDON2) return gates::P2_NUM_CONSTRAINTS;
-    if (kind == GL_GATE_U32_ARITHMETIC) return (int)((4 + gates::U32_LIMBS) * param);
-    return -1;
+    if (gate_wires(kind, param) < 0) return -1;
+    const uint32_t lo = param & 0xFF, hi = param >> 8;
+    switch (kind) {
+        case GL_GATE_POSEIDON2: return gates::P2_NUM_CONSTRAINTS;
+        case GL_GATE_U32_ARITHMETIC: return (int)((4 + gates::U32_LIMBS) * param);
+        case GL_GATE_U32_ADD_MANY: return (int)(21 * hi);
+        case GL_GATE_U32_SUBTRACTION: return (int)(19 * param);
+        case GL_GATE_U32_RANGE_CHECK: return (int)(17 * param);
+        case GL_GATE_U32_INTERLEAVE: return (int)(34 * param);
+        case GL_GATE_UNINTERLEAVE_TO_U32:
+        case GL_GATE_UNINTERLEAVE_TO_B32: return (int)(67 * param);
+        default: return (int)(2 + 5 * hi + 1 + ((lo + hi - 1) / hi + 1) + 2);
+    }
 }
 void check_gate(int kind, uint32_t param) {
-    if (kind != GL_GATE_POSEIDON2 && kind != GL_GATE_U32_ARITHMETIC) GL_THROW(GL_ERR_INVALID, "unknown gate kind %d", kind);
-    if (kind == GL_GATE_U32_ARITHMETIC && (param == 0 || param > 3)) GL_THROW(GL_ERR_INVALID, "U32ArithmeticGate: num_ops must be 1..3");
+    if (kind < GL_GATE_POSEIDON2 || kind > GL_GATE_COMPARISON) GL_THROW(GL_ERR_INVALID, "unknown gate kind %d", kind);
+    if (gate_wires(kind, param) < 0) GL_THROW(GL_ERR_INVALID, "gate kind %d: parameter %u out of range (see include/gl_commit.h)", kind, param);
 }
 Quotient* find_quotient(gl_ctx* c, gl_handle h) {
     auto it = c->quotients.find(h);

@@ -75,6 +75,51 @@ def _rows(kind, n, seed):
     return np.array(rows, dtype=np.uint64)
 
 
+def _other_gate_case(kind, param, rnd):
+    """(valid witness row, oracle evaluator) for the u32 / b32 gates 2..8"""
+    u = lambda: rnd.getrandbits(32)
+    lo, hi = param & 0xFF, param >> 8
+    if kind == 2:
+        return go.add_many_witness([([u() for _ in range(lo)], rnd.randrange(4)) for _ in range(hi)], lo), lambda w: go.add_many_eval(w, lo, hi)
+    if kind == 3:
+        return go.subtraction_witness([(u(), u(), rnd.randrange(2)) for _ in range(param)]), lambda w: go.subtraction_eval(w, param)
+    if kind == 4:
+        return go.range_check_witness([u() for _ in range(param)]), lambda w: go.range_check_eval(w, param)
+    if kind == 5:
+        return go.interleave_witness([u() for _ in range(param)]), lambda w: go.interleave_eval(w, param)
+    if kind in (6, 7):
+        return go.uninterleave_witness([rnd.getrandbits(63) for _ in range(param)], kind == 7), lambda w: go.uninterleave_eval(w, param, kind == 7)
+    a, b = (u(), u()) if rnd.random() < 0.7 else (7, 7)
+    return go.comparison_witness(a & ((1 << lo) - 1), b & ((1 << lo) - 1), lo, hi), lambda w: go.comparison_eval(w, lo, hi)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,param", [(2, 5 | 5 << 8), (2, 24 | 1 << 8), (3, 6), (3, 1), (4, 7), (5, 3), (6, 2), (7, 2), (7, 1), (8, 32 | 16 << 8),
+                                        (8, 10 | 2 << 8)])
+def test_other_u32_gates_match_oracle(ctx, kind, param):
+    """the reference's remaining gates (src/common/u32/gates/{add_many_u32,subtraction_u32,range_check_u32,interleave_u32,
+    uninterleave_to_u32,uninterleave_to_b32,comparison}.rs): every constraint of valid, tampered and arbitrary rows"""
+    lib, rnd = ctx.lib, random.Random(1000 * kind + param)
+    nw, nc = lib.gl_gate_num_wires(kind, param), lib.gl_gate_num_constraints(kind, param)
+    rows, evalf = [], None
+    for r in range(48):
+        w, evalf = _other_gate_case(kind, param, rnd)
+        w = w[:nw]
+        assert not any(evalf(w)), "the oracle's own witness must satisfy the gate"
+        if r % 3 == 1:
+            w[rnd.randrange(nw)] = rnd.randrange(P)
+        if r % 3 == 2:
+            w = [rnd.getrandbits(64) for _ in range(nw)]
+        rows.append(w)
+    rows = np.array(rows, dtype=np.uint64)
+    assert len(evalf(rows[0].tolist())) == nc
+    out = np.zeros((rows.shape[0], nc), dtype=np.uint64)
+    assert lib.gl_gate_eval_rows(ctx.handle, kind, param, rows.ctypes.data, rows.shape[0], out.ctypes.data) == 0
+    for r in range(rows.shape[0]):
+        assert out[r].tolist() == evalf(rows[r].tolist()), r
+    assert lib.gl_gate_num_wires(kind, 0) == -1 or kind == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,param", [(0, 0), (1, 3), (1, 1)])
 def test_gate_constraints_match_oracle(ctx, kind, param):
