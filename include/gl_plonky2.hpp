@@ -644,7 +644,116 @@ private:
         return b;
     }
     mutable std::vector<PolynomialCoeffs> polys_;
+
+public:
+    /* wrap a batch handle the library produced elsewhere (gl_quotient_commit) */
+    static PolynomialBatch adopt(Context& c, gl_handle h, MerkleCap cap, size_t degree_log, size_t rate_bits) {
+        PolynomialBatch b;
+        b.merkle_tree = MerkleTree(c, h, std::move(cap));
+        b.degree_log = degree_log;
+        b.rate_bits = rate_bits;
+        b.blinding = false;
+        return b;
+    }
 };
+
+
+/* ------------------------------------------------------------------------------------------------ quotient / permutation / witness */
+/* SURVEY §8(f) ranks 3-4.  Gate kinds are include/gl_commit.h's GL_GATE_* (the reference's own gates: Poseidon2Gate and the eight
+ * u32 / b32 gates under /root/reference/src/common/u32/gates/). */
+
+/* Gate::eval_unfiltered_base_batch on host rows: rows = n x num_wires words -> n x num_constraints constraint values */
+inline std::vector<F> evaluate_gate_constraints(int kind, uint32_t param, const std::vector<F>& rows, Context* ctx = nullptr) {
+    Context& c = ctx_or_default(ctx);
+    const int nw = gl_gate_num_wires(kind, param), nc = gl_gate_num_constraints(kind, param);
+    if (nw <= 0 || nc <= 0) throw Panic("unknown gate kind / parameter");
+    if (rows.size() % size_t(nw)) throw Panic("rows must be n * num_wires words");
+    const size_t n = rows.size() / size_t(nw);
+    std::vector<F> out(n * size_t(nc));
+    c.check(gl_gate_eval_rows(c.raw(), kind, param, rows.data(), n, out.data()));
+    return out;
+}
+
+/* the gate part of plonky2 plonk/prover.rs · compute_quotient_polys over the resident LDE rows of the wires commit, and its tail
+ * (divide by Z_H on the coset, coset_ifft, chunks(degree), PolynomialBatch::from_coeffs) */
+class QuotientAccumulator {
+public:
+    QuotientAccumulator(const PolynomialBatch& wires, size_t num_challenges, Context* ctx = nullptr);
+    ~QuotientAccumulator() { if (h_) gl_quotient_end(ctx_->raw(), h_); }
+    QuotientAccumulator(const QuotientAccumulator&) = delete;
+    QuotientAccumulator& operator=(const QuotientAccumulator&) = delete;
+    /* acc[k][row] += filter(row) * sum_i alphas[k]^(constraint_offset + i) * constraint_i(row) */
+    void add_gate(int kind, uint32_t param, const std::vector<F>& alphas, size_t constraint_offset = 0, const PolynomialBatch* filter_batch = nullptr,
+                  size_t filter_col = 0);
+    std::vector<F> values() const {                       /* [num_challenges][R], row order = the leaves' */
+        std::vector<F> out(n_challenges_ * n_rows_);
+        ctx_->check(gl_quotient_read(ctx_->raw(), h_, out.data()));
+        return out;
+    }
+    PolynomialBatch commit(size_t cap_height);            /* quotient_polys_commitment */
+
+private:
+    Context* ctx_;
+    gl_handle h_ = 0;
+    size_t n_challenges_, n_rows_, degree_log_, rate_bits_;
+};
+
+/* plonk/prover.rs · all_wires_permutation_partial_products, columns in prove()'s order (Z of every challenge first) */
+inline std::vector<PolynomialValues> partial_products_and_zs(const std::vector<PolynomialValues>& wires, const std::vector<PolynomialValues>& sigmas,
+                                                             const std::vector<F>& k_is, const std::vector<F>& betas, const std::vector<F>& gammas,
+                                                             size_t degree, Context* ctx = nullptr) {
+    Context& c = ctx_or_default(ctx);
+    if (wires.empty() || wires.size() != sigmas.size() || wires.size() != k_is.size()) throw Panic("partial_products: one sigma and one k_i per routed wire");
+    if (betas.empty() || betas.size() != gammas.size()) throw Panic("partial_products: one (beta, gamma) per challenge");
+    if (degree == 0) throw Panic("partial_products: degree must be positive");
+    const size_t n = wires[0].len();
+    if (n == 0 || (n & (n - 1))) throw Panic("partial_products: polynomial length must be a power of two");
+    std::vector<const uint64_t*> wp, sp;
+    for (size_t j = 0; j < wires.size(); j++) {
+        if (wires[j].len() != n || sigmas[j].len() != n) throw Panic("Polynomial degrees inconsistent");
+        wp.push_back(wires[j].values.data());
+        sp.push_back(sigmas[j].values.data());
+    }
+    size_t log_n = 0;
+    while ((size_t(1) << log_n) < n) log_n++;
+    const size_t n_chunks = (wires.size() + degree - 1) / degree, n_out = betas.size() * n_chunks;
+    std::vector<F> flat(n_out * n);
+    c.check(gl_partial_products(c.raw(), wp.data(), sp.data(), uint32_t(wires.size()), uint32_t(log_n), k_is.data(), betas.data(), gammas.data(),
+                                uint32_t(betas.size()), uint32_t(degree), flat.data()));
+    std::vector<PolynomialValues> out(n_out);
+    for (size_t j = 0; j < n_out; j++) out[j].values.assign(flat.begin() + j * n, flat.begin() + (j + 1) * n);
+    return out;
+}
+
+/* /root/reference/src/common/poseidon2/poseidon2_gate.rs:447-523 · Poseidon2Generator::run_once for n rows: inputs n x 13 -> n x 135 */
+inline std::vector<F> poseidon2_gate_witness(const std::vector<F>& inputs, Context* ctx = nullptr) {
+    Context& c = ctx_or_default(ctx);
+    if (inputs.size() % 13) throw Panic("poseidon2_gate_witness: inputs must be n * 13 words (12 state inputs + swap)");
+    const size_t n = inputs.size() / 13;
+    std::vector<F> out(n * 135);
+    c.check(gl_poseidon2_gate_witness(c.raw(), inputs.data(), n, out.data()));
+    return out;
+}
+
+inline QuotientAccumulator::QuotientAccumulator(const PolynomialBatch& wires, size_t num_challenges, Context* ctx)
+    : ctx_(&ctx_or_default(ctx)), n_challenges_(num_challenges), n_rows_(wires.merkle_tree.n_leaves()), degree_log_(wires.degree_log),
+      rate_bits_(wires.rate_bits) {
+    ctx_->check(gl_quotient_begin(ctx_->raw(), wires.merkle_tree.handle(), uint32_t(num_challenges), &h_));
+}
+inline void QuotientAccumulator::add_gate(int kind, uint32_t param, const std::vector<F>& alphas, size_t constraint_offset,
+                                          const PolynomialBatch* filter_batch, size_t filter_col) {
+    if (alphas.size() != n_challenges_) throw Panic("QuotientAccumulator::add_gate: one alpha per challenge expected");
+    ctx_->check(gl_quotient_add_gate(ctx_->raw(), h_, kind, param, alphas.data(), uint32_t(constraint_offset),
+                                     filter_batch ? filter_batch->merkle_tree.handle() : 0, uint32_t(filter_col)));
+}
+inline PolynomialBatch QuotientAccumulator::commit(size_t cap_height) {
+    if (cap_height > degree_log_ + rate_bits_) throw Panic("cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())");
+    MerkleCap cap;
+    cap.hashes.resize(size_t(1) << cap_height);
+    gl_handle h = 0;
+    ctx_->check(gl_quotient_commit(ctx_->raw(), h_, uint32_t(cap_height), cap.hashes[0].elements.data(), &h));
+    return PolynomialBatch::adopt(*ctx_, h, std::move(cap), degree_log_, rate_bits_);
+}
 
 }  // namespace plonky2
 #endif /* GL_PLONKY2_HPP */

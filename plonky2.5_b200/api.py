@@ -525,3 +525,113 @@ def fri_prover_query_rounds(initial_merkle_trees: Sequence[MerkleTree], trees: S
             rnd["steps"].append({"evals": rows[q].reshape(-1, 2).copy(), "merkle_proof": sib[q]})
         out.append(rnd)
     return out
+
+
+# ---- gate constraints over the resident LDE rows, partial products / Z, witness rows -------------------------
+GATE_POSEIDON2, GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_RANGE_CHECK = 0, 1, 2, 3, 4
+GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32, GATE_COMPARISON = 5, 6, 7, 8
+
+
+def gate_shape(kind: int, param: int = 0) -> Tuple[int, int]:
+    """(num_wires, num_constraints) of a gate (Gate::num_wires / num_constraints); ValueError for an unknown kind or parameter"""
+    lib = _lib.load()
+    nw, nc = lib.gl_gate_num_wires(kind, param), lib.gl_gate_num_constraints(kind, param)
+    if nw < 0 or nc < 0:
+        raise ValueError(f"unknown gate kind {kind} / parameter {param}")
+    return nw, nc
+
+
+def evaluate_gate_constraints(kind: int, param: int, rows, ctx: Optional[Context] = None) -> np.ndarray:
+    """Gate::eval_unfiltered_base_batch for host rows [n][num_wires]: every constraint value, uncombined ([n][num_constraints])"""
+    ctx = ctx or default_context()
+    nw, nc = gate_shape(kind, param)
+    r = np.ascontiguousarray(rows, dtype=np.uint64)
+    if r.ndim != 2 or r.shape[1] != nw:
+        raise ValueError(f"rows must be [n][{nw}]")
+    out = np.zeros((r.shape[0], nc), dtype=np.uint64)
+    _check(ctx, ctx.lib.gl_gate_eval_rows(ctx.handle, kind, param, _ptr(r), r.shape[0], _ptr(out)))
+    return out
+
+
+class Quotient:
+    """The gate part of plonky2 plonk/prover.rs · compute_quotient_polys on the device: for every LDE row of the committed wires batch,
+    acc[k] += filter * sum_i alpha_k^(offset + i) * constraint_i (evaluate_gate_constraints_base_batch + reduce_with_powers), then
+    `commit` = divide by Z_H on the coset, coset_ifft, split into 2^rate_bits chunks, PolynomialBatch::from_coeffs."""
+
+    def __init__(self, wires: "PolynomialBatch", n_challenges: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or wires.ctx
+        self.wires, self.n_challenges = wires, n_challenges
+        h = c_uint64()
+        _check(self.ctx, self.ctx.lib.gl_quotient_begin(self.ctx.handle, wires.merkle_tree._h, n_challenges, byref(h)))
+        self._h = h.value
+
+    def add_gate(self, kind: int, param: int, alphas, constraint_offset: int = 0, filter: Optional[Tuple["PolynomialBatch", int]] = None) -> float:
+        """returns the kernel time in ms (CUDA events)"""
+        a = np.ascontiguousarray(alphas, dtype=np.uint64).reshape(-1)
+        if a.size != self.n_challenges:
+            raise ValueError("one alpha per challenge expected")
+        fb, fc = (filter[0].merkle_tree._h, int(filter[1])) if filter is not None else (0, 0)
+        _check(self.ctx, self.ctx.lib.gl_quotient_add_gate(self.ctx.handle, self._h, kind, param, _ptr(a), constraint_offset, fb, fc))
+        ms = ctypes.c_float()
+        self.ctx.lib.gl_ctx_aux_ms(self.ctx.handle, byref(ms))
+        return float(ms.value)
+
+    def values(self) -> np.ndarray:
+        """[n_challenges][R] accumulated values, row order = the leaves' (row i = LDE point bitrev(i))"""
+        out = np.zeros((self.n_challenges, self.wires.merkle_tree.n_leaves), dtype=np.uint64)
+        _check(self.ctx, self.ctx.lib.gl_quotient_read(self.ctx.handle, self._h, _ptr(out)))
+        return out
+
+    def commit(self, cap_height: int) -> "PolynomialBatch":
+        """quotient_polys_commitment: n_challenges * 2^rate_bits chunk polynomials of N coefficients, committed with from_coeffs"""
+        t = self.wires.merkle_tree
+        if cap_height > t.degree_log + t.rate_bits:
+            raise ValueError(f"cap_height={cap_height} should be at most log2(leaves.len())={t.degree_log + t.rate_bits}")
+        cap = np.zeros(4 << cap_height, dtype=np.uint64)
+        h = c_uint64()
+        _check(self.ctx, self.ctx.lib.gl_quotient_commit(self.ctx.handle, self._h, cap_height, _ptr(cap), byref(h)))
+        return PolynomialBatch(self.ctx, MerkleTree(self.ctx, h.value, cap), self.n_challenges << t.rate_bits)
+
+    def free(self):
+        if self._h and self.ctx.handle:
+            self.ctx.lib.gl_quotient_end(self.ctx.handle, self._h)
+        self._h = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def partial_products_and_zs(wire_cols, sigma_cols, k_is, betas, gammas, degree: int, ctx: Optional[Context] = None) -> np.ndarray:
+    """plonky2 plonk/prover.rs · all_wires_permutation_partial_products with prove()'s "Z first" order: wire_cols / sigma_cols are the
+    routed wires' witness values and the sigma polynomials' values on the subgroup ([n_routed][N]); returns [(n_ch * n_chunks)][N]."""
+    ctx = ctx or default_context()
+    w, log_n = PolynomialBatch._cols(wire_cols)
+    s, log_s = PolynomialBatch._cols(sigma_cols)
+    if len(w) != len(s) or log_n != log_s:
+        raise ValueError("wires and sigmas must have the same shape")
+    k = np.ascontiguousarray(k_is, dtype=np.uint64).reshape(-1)
+    b = np.ascontiguousarray(betas, dtype=np.uint64).reshape(-1)
+    g = np.ascontiguousarray(gammas, dtype=np.uint64).reshape(-1)
+    if k.size != len(w) or b.size != g.size or b.size == 0:
+        raise ValueError("k_is must have one entry per routed wire; betas and gammas one per challenge")
+    n_chunks = -(-len(w) // degree)
+    out = np.zeros((b.size * n_chunks, 1 << log_n), dtype=np.uint64)
+    wp = (c_void_p * len(w))(*[c.ctypes.data for c in w])
+    sp = (c_void_p * len(s))(*[c.ctypes.data for c in s])
+    _check(ctx, ctx.lib.gl_partial_products(ctx.handle, wp, sp, len(w), log_n, _ptr(k), _ptr(b), _ptr(g), b.size, degree, _ptr(out)))
+    return out
+
+
+def poseidon2_gate_witness(inputs, ctx: Optional[Context] = None) -> np.ndarray:
+    """Poseidon2Generator::run_once (/root/reference/src/common/poseidon2/poseidon2_gate.rs:447-523) for a batch of gate rows:
+    inputs [n][13] = 12 state inputs + swap flag -> [n][135] wires"""
+    ctx = ctx or default_context()
+    x = np.ascontiguousarray(inputs, dtype=np.uint64)
+    if x.ndim != 2 or x.shape[1] != 13:
+        raise ValueError("inputs must be [n][13]")
+    out = np.zeros((x.shape[0], 135), dtype=np.uint64)
+    _check(ctx, ctx.lib.gl_poseidon2_gate_witness(ctx.handle, _ptr(x), x.shape[0], _ptr(out)))
+    return out

@@ -193,6 +193,58 @@ impl Context {
     }
 
     /// `prove_openings`, front half: start accumulating `final_poly` over batches of degree 2^log_n
+    /// `Gate::eval_unfiltered_base_batch` on host rows (`rows.len() = n * num_wires`): every constraint value, uncombined.
+    /// `kind` is one of `ffi::GL_GATE_*` (the reference's Poseidon2Gate and u32 / b32 gates), `param` as documented in the header.
+    pub fn evaluate_gate_constraints(&self, kind: i32, param: u32, rows: &[u64]) -> Result<Vec<u64>, Error> {
+        let (nw, nc) = unsafe { (ffi::gl_gate_num_wires(kind as c_int, param), ffi::gl_gate_num_constraints(kind as c_int, param)) };
+        if nw <= 0 || nc <= 0 || rows.len() % nw as usize != 0 {
+            return Err(Error::Invalid("unknown gate kind / parameter, or rows is not n * num_wires words".into()));
+        }
+        let n = rows.len() / nw as usize;
+        let mut out = vec![0u64; n * nc as usize];
+        self.check(unsafe { ffi::gl_gate_eval_rows(self.raw, kind as c_int, param, rows.as_ptr(), n as u64, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+
+    /// the gate part of `plonk/prover.rs · compute_quotient_polys` over the resident LDE rows of the wires commit
+    pub fn quotient_begin<'c>(&'c self, wires: &DeviceTree<'c>, num_challenges: usize) -> Result<Quotient<'c>, Error> {
+        let mut h: ffi::gl_handle = 0;
+        self.check(unsafe { ffi::gl_quotient_begin(self.raw, wires.handle, num_challenges as u32, &mut h) })?;
+        Ok(Quotient { ctx: self, handle: h, num_challenges })
+    }
+
+    /// `plonk/prover.rs · all_wires_permutation_partial_products` in `prove()`'s column order (the Z of every challenge first);
+    /// returns `num_challenges * ceil(n_routed / degree)` columns of `N` values, flattened.
+    pub fn partial_products_and_zs(&self, wires: &[&[u64]], sigmas: &[&[u64]], k_is: &[u64], betas: &[u64], gammas: &[u64],
+                                   degree: usize) -> Result<Vec<u64>, Error> {
+        let n = wires.first().map(|c| c.len()).ok_or_else(|| Error::Invalid("no routed wires".into()))?;
+        if !n.is_power_of_two() || wires.len() != sigmas.len() || wires.len() != k_is.len() || betas.len() != gammas.len() || betas.is_empty()
+            || degree == 0 || wires.iter().chain(sigmas.iter()).any(|c| c.len() != n)
+        {
+            return Err(Error::Invalid("partial_products_and_zs: inconsistent shapes".into()));
+        }
+        let wp: Vec<*const u64> = wires.iter().map(|c| c.as_ptr()).collect();
+        let sp: Vec<*const u64> = sigmas.iter().map(|c| c.as_ptr()).collect();
+        let n_chunks = (wires.len() + degree - 1) / degree;
+        let mut out = vec![0u64; betas.len() * n_chunks * n];
+        self.check(unsafe {
+            ffi::gl_partial_products(self.raw, wp.as_ptr(), sp.as_ptr(), wires.len() as u32, n.trailing_zeros(), k_is.as_ptr(), betas.as_ptr(),
+                                     gammas.as_ptr(), betas.len() as u32, degree as u32, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+
+    /// `Poseidon2Generator::run_once` for `inputs.len() / 13` gate rows (12 state inputs + swap flag each) -> 135 wires per row
+    pub fn poseidon2_gate_witness(&self, inputs: &[u64]) -> Result<Vec<u64>, Error> {
+        if inputs.len() % 13 != 0 {
+            return Err(Error::Invalid("inputs must be n * 13 words".into()));
+        }
+        let n = inputs.len() / 13;
+        let mut out = vec![0u64; n * 135];
+        self.check(unsafe { ffi::gl_poseidon2_gate_witness(self.raw, inputs.as_ptr(), n as u64, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+
     pub fn openings_begin(&self, log_n: usize) -> Result<Openings<'_>, Error> {
         let mut h: ffi::gl_handle = 0;
         self.check(unsafe { ffi::gl_openings_begin(self.raw, log_n as u32, &mut h) })?;
@@ -406,6 +458,38 @@ impl Drop for Openings<'_> {
 }
 
 /// Pinned host memory for outputs that must be materialised on the host (INTEGRATION.md "Host memory for copy-back")
+/// accumulator of `sum_i alpha_k^(offset + i) * constraint_i` over every LDE row of a wires commit (`gl_quotient_*`)
+pub struct Quotient<'c> {
+    ctx: &'c Context,
+    handle: ffi::gl_handle,
+    num_challenges: usize,
+}
+
+impl<'c> Quotient<'c> {
+    pub fn add_gate(&mut self, kind: i32, param: u32, alphas: &[u64], constraint_offset: usize, filter: Option<(&DeviceTree<'c>, usize)>) -> Result<(), Error> {
+        assert_eq!(alphas.len(), self.num_challenges, "one alpha per challenge");
+        let (fb, fc) = filter.map(|(t, c)| (t.handle, c as u32)).unwrap_or((0, 0));
+        self.ctx.check(unsafe { ffi::gl_quotient_add_gate(self.ctx.raw, self.handle, kind as c_int, param, alphas.as_ptr(), constraint_offset as u32, fb, fc) })
+    }
+
+    /// divide by Z_H on the coset, coset_ifft, chunks(degree), `PolynomialBatch::from_coeffs`: the quotient commitment
+    pub fn commit(&self, cap_height: usize) -> Result<DeviceTree<'c>, Error> {
+        if cap_height > 31 {
+            return Err(Error::Invalid(format!("cap_height={cap_height} should be at most log2(leaves.len())")));
+        }
+        let mut cap = vec![[0u64; 4]; 1 << cap_height];
+        let mut h: ffi::gl_handle = 0;
+        self.ctx.check(unsafe { ffi::gl_quotient_commit(self.ctx.raw, self.handle, cap_height as u32, cap.as_mut_ptr() as *mut u64, &mut h) })?;
+        DeviceTree::adopt(self.ctx, h, cap)
+    }
+}
+
+impl Drop for Quotient<'_> {
+    fn drop(&mut self) {
+        unsafe { ffi::gl_quotient_end(self.ctx.raw, self.handle) };
+    }
+}
+
 pub struct PinnedBuf {
     ptr: *mut u64,
     words: usize,

@@ -142,14 +142,12 @@ def test_poseidon2_gate_witness_matches_generator(ctx):
     inp = np.array([[rnd.randrange(P) for _ in range(12)] + [rnd.randrange(2)] for _ in range(64)], dtype=np.uint64)
     inp[5, :12] = np.uint64(P - 1)
     inp[6, :12] = 0
-    out = np.zeros((64, 135), dtype=np.uint64)
-    assert ctx.lib.gl_poseidon2_gate_witness(ctx.handle, inp.ctypes.data, 64, out.ctypes.data) == 0
+    import plonky25_b200 as g
+    out = g.poseidon2_gate_witness(inp, ctx=ctx)
     for r in range(64):
         assert out[r].tolist() == go.poseidon2_gate_witness(inp[r, :12].tolist(), int(inp[r, 12])), r
     # and the generated rows satisfy the gate on the device
-    c = np.zeros((64, 123), dtype=np.uint64)
-    assert ctx.lib.gl_gate_eval_rows(ctx.handle, 0, 0, out.ctypes.data, 64, c.ctypes.data) == 0
-    assert not c.any()
+    assert not g.evaluate_gate_constraints(g.GATE_POSEIDON2, 0, out, ctx=ctx).any()
 
 
 @pytest.mark.gpu
@@ -217,13 +215,9 @@ def test_partial_products_and_zs_match_oracle(ctx, log_n, n_routed, degree, n_ch
     n_chunks = -(-n_routed // degree)
     W, S = np.array(wires, dtype=np.uint64), np.array(sigmas, dtype=np.uint64)
     W[0, 0] += np.uint64(P) if int(W[0, 0]) < 2**32 - 1 else np.uint64(0)     # a non-canonical input word
-    out = np.zeros((n_ch * n_chunks, n), dtype=np.uint64)
-    wp_ = (ctypes.c_void_p * n_routed)(*[W[j].ctypes.data for j in range(n_routed)])
-    sp_ = (ctypes.c_void_p * n_routed)(*[S[j].ctypes.data for j in range(n_routed)])
-    k = np.array(k_is, dtype=np.uint64); b = np.array(betas, dtype=np.uint64); gm = np.array(gammas, dtype=np.uint64)
-    rc = ctx.lib.gl_partial_products(ctx.handle, wp_, sp_, n_routed, log_n, k.ctypes.data, b.ctypes.data, gm.ctypes.data, n_ch, degree,
-                                     out.ctypes.data)
-    assert rc == 0, ctx.lib.gl_ctx_last_error(ctx.handle).decode()
+    import plonky25_b200 as g
+    out = g.partial_products_and_zs(list(W), list(S), k_is, betas, gammas, degree, ctx=ctx)
+    assert out.shape == (n_ch * n_chunks, n)
     assert out.tolist() == want
     # the permutation argument closes: Z(x_0) = 1 and Z(x_{n-1}) * (last row's chunk products) = 1
     for c in range(n_ch):
@@ -248,17 +242,12 @@ def test_quotient_commit_tail(ctx, oc, log_n):
     n, R, bits = 1 << log_n, 1 << (log_n + 3), log_n + 3
     wires = g.PolynomialBatch.from_values(list(splitmix_columns(90 + log_n, 135, n)), r, False, h, ctx=ctx)
     alphas = np.array([11, 0xABCDEF0123456789 % P], dtype=np.uint64)
-    q = ctypes.c_uint64()
-    assert lib.gl_quotient_begin(ctx.handle, wires.merkle_tree._h, n_ch, ctypes.byref(q)) == 0
-    assert lib.gl_quotient_add_gate(ctx.handle, q.value, 0, 0, alphas.ctypes.data, 0, 0, 0) == 0
-    acc = np.zeros((n_ch, R), dtype=np.uint64)
-    assert lib.gl_quotient_read(ctx.handle, q.value, acc.ctypes.data) == 0
-    cap = np.zeros((1 << h, 4), dtype=np.uint64)
-    hb = ctypes.c_uint64()
-    rc = lib.gl_quotient_commit(ctx.handle, q.value, h, cap.ctypes.data, ctypes.byref(hb))
-    assert rc == 0, lib.gl_ctx_last_error(ctx.handle).decode()
-    lib.gl_quotient_end(ctx.handle, q.value)
-    batch = g.PolynomialBatch(ctx, g.MerkleTree(ctx, hb.value, cap.reshape(-1)), n_ch * 8)
+    quot = g.Quotient(wires, n_ch, ctx=ctx)                     # the Python mirror of the reference-facing interface
+    quot.add_gate(g.GATE_POSEIDON2, 0, alphas)
+    acc = quot.values()
+    batch = quot.commit(h)
+    quot.free()
+    cap = batch.merkle_tree.cap.hashes
     chunks = batch.polynomials                                  # [16][N] coefficients
     # (a) oracle: divide by Z_H, interpolate on the coset, split
     rev = np.array([int(format(i, "0%db" % bits)[::-1], 2) for i in range(R)])

@@ -138,7 +138,7 @@ def build_cpp_tools() -> dict:
     lib, ora = g.build(), build_oracle()
     os.makedirs(OUT_DIR, exist_ok=True)
     out = {"cbench": os.path.join(OUT_DIR, "cbench"), "variant_bench": os.path.join(OUT_DIR, "variant_bench"),
-           "devbench": os.path.join(OUT_DIR, "devbench")}
+           "devbench": os.path.join(OUT_DIR, "devbench"), "gates_mirror_test": os.path.join(OUT_DIR, "gates_mirror_test")}
     hdr = os.path.join(ROOT, "include", "gl_commit.h")
 
     def stale(exe, deps):
@@ -147,6 +147,9 @@ def build_cpp_tools() -> dict:
     src = os.path.join(ROOT, "tools", "cbench.cpp")
     if stale(out["cbench"], [src, hdr, lib]):
         _cxx([src, "-o", out["cbench"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
+    src = os.path.join(ROOT, "tests", "cpp", "gates_mirror_test.cpp")
+    if stale(out["gates_mirror_test"], [src, hdr, os.path.join(ROOT, "include", "gl_plonky2.hpp"), lib]):
+        _cxx([src, "-o", out["gates_mirror_test"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
     src = os.path.join(ROOT, "tools", "devbench.cpp")
     if stale(out["devbench"], [src, hdr, lib]):
         _cxx([src, "-o", out["devbench"], "-L", os.path.dirname(lib), "-lgl_commit", "-Wl,-rpath,$ORIGIN/../../../plonky2.5_b200", "-pthread"])
@@ -188,3 +191,11 @@ def test_cpp_host_mirror_matches_oracle_on_gpu(tmp_path):
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "ALL OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_gates_mirror_on_gpu():
+    """QuotientAccumulator / partial_products_and_zs / poseidon2_gate_witness of include/gl_plonky2.hpp against their own identities"""
+    exe = build_cpp_tools()["gates_mirror_test"]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
