@@ -194,7 +194,7 @@ impl Context {
 
     /// `prove_openings`, front half: start accumulating `final_poly` over batches of degree 2^log_n
     /// `Gate::eval_unfiltered_base_batch` on host rows (`rows.len() = n * num_wires`): every constraint value, uncombined.
-    /// `kind` is one of `ffi::GL_GATE_*` (the reference's Poseidon2Gate and u32 / b32 gates), `param` as documented in the header.
+    /// `kind` is one of the gate constants of `ffi` (`ffi::GL_GATE_POSEIDON2`, `ffi::GL_GATE_U32_ARITHMETIC`, ...: the reference's Poseidon2Gate and u32 / b32 gates), `param` as documented in the header.
     pub fn evaluate_gate_constraints(&self, kind: i32, param: u32, rows: &[u64]) -> Result<Vec<u64>, Error> {
         let (nw, nc) = unsafe { (ffi::gl_gate_num_wires(kind as c_int, param), ffi::gl_gate_num_constraints(kind as c_int, param)) };
         if nw <= 0 || nc <= 0 || rows.len() % nw as usize != 0 {
