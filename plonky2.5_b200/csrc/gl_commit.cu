@@ -184,7 +184,8 @@ struct gl_ctx {
     std::map<uint64_t, std::unique_ptr<std::vector<CosetTable>>> lde_tables;  // (log_n, rate_bits) -> per coset
     std::map<std::pair<uint64_t, uint32_t>, std::unique_ptr<CosetTable>> coset_cache;   // (shift, log_len) -> g^j: FRI layers / final-poly LDE
     size_t coset_cache_words = 0;
-    DevBuf in_stage, vals, scratch;
+    DevBuf in_stage, vals, scratch, hash_state;
+    bool stream_hash = true;              // GL_STREAM_HASH=0: hash the leaves in one launch after the whole LDE even for host columns
     std::map<gl_handle, std::unique_ptr<Tree>> trees;
     std::map<gl_handle, std::unique_ptr<Fri>> fris;
     std::map<gl_handle, std::unique_ptr<Openings>> openings;
@@ -453,28 +454,44 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
     }
 }
 
+#ifndef LEAF_BLOCK
+#define LEAF_BLOCK 128
+#endif
+// the tree above the leaf digests: layers 1..log_sub, one launch per layer
+void merkle_levels(gl_ctx* c, uint64_t n_leaves, uint32_t cap_height, uint64_t* d_digests, uint64_t* d_cap, uint32_t* tree_launches) {
+    const uint32_t log_sub = log2_exact(n_leaves) - cap_height;
+    for (uint32_t layer = 1; layer <= log_sub; layer++) {
+        uint64_t n_nodes = n_leaves >> layer;
+        constexpr int TB = 128;
+        merkle::tree_level_kernel<TB><<<(uint32_t)((n_nodes + TB - 1) / TB), TB, 0, c->stream>>>(d_digests, d_cap, layer, log_sub, n_nodes);
+        CUDA_CHECK(cudaGetLastError());
+        if (tree_launches) (*tree_launches)++;
+    }
+}
+
 void merkle_build(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch,
                   uint32_t cap_height, uint64_t* d_digests, uint64_t* d_cap, uint32_t* leaf_launches,
                   uint32_t* tree_launches, cudaEvent_t after_leaves) {
     uint32_t log_leaves = log2_exact(n_leaves);
     uint32_t log_sub = log_leaves - cap_height;
-#ifndef LEAF_BLOCK
-#define LEAF_BLOCK 128
-#endif
     constexpr int LB = LEAF_BLOCK;
     merkle::leaf_hash_kernel<LB><<<(uint32_t)((n_leaves + LB - 1) / LB), LB, 0, c->stream>>>(
         d_leaves, pitch, leaf_len, n_leaves, log_sub, d_digests, d_cap);
     CUDA_CHECK(cudaGetLastError());
     if (leaf_launches) (*leaf_launches)++;
     if (after_leaves) CUDA_CHECK(cudaEventRecord(after_leaves, c->stream));
-    for (uint32_t layer = 1; layer <= log_sub; layer++) {
-        uint64_t n_nodes = n_leaves >> layer;
-        constexpr int TB = 128;
-        merkle::tree_level_kernel<TB><<<(uint32_t)((n_nodes + TB - 1) / TB), TB, 0, c->stream>>>(d_digests, d_cap, layer,
-                                                                                               log_sub, n_nodes);
-        CUDA_CHECK(cudaGetLastError());
-        if (tree_launches) (*tree_launches)++;
-    }
+    merkle_levels(c, n_leaves, cap_height, d_digests, d_cap, tree_launches);
+}
+
+// streaming leaf sponge (merkle.cuh · leaf_absorb_kernel): columns [col0, col1) of every leaf
+void leaf_absorb(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch, uint32_t cap_height, uint32_t col0,
+                 uint32_t col1, uint64_t* d_state, uint64_t* d_digests, uint64_t* d_cap, bool first, bool last, uint32_t* leaf_launches) {
+    const uint32_t log_sub = log2_exact(n_leaves) - cap_height;
+    constexpr int LB = LEAF_BLOCK;
+    merkle::leaf_absorb_kernel<LB><<<(uint32_t)((n_leaves + LB - 1) / LB), LB, 0, c->stream>>>(d_leaves, pitch, leaf_len, col0, col1, n_leaves, log_sub,
+                                                                                             d_state, d_digests, d_cap, first ? 1 : 0, last ? 1 : 0);
+    CUDA_CHECK(cudaGetLastError());
+    if (leaf_launches) (*leaf_launches)++;
 }
 
 void check_shape(uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height) {
@@ -610,12 +627,15 @@ void lde_stage(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t 
 // independent polynomials).  Chunks grow 8, 16, 24, 24, ... columns: only the small first copy is exposed.  Chunk offsets
 // are multiples of 8.  With pinned host memory the copies overlap completely.
 template <class F>
-void for_each_host_chunk(gl_ctx* c, const uint64_t* const* host_cols, uint32_t n_cols, uint64_t N, F&& fn) {
+void for_each_host_chunk(gl_ctx* c, const uint64_t* const* host_cols, uint32_t n_cols, uint64_t N, F&& fn, bool doubling = false) {
     for (uint32_t j = 0; j < n_cols; j++)
         if (!host_cols[j]) GL_THROW(GL_ERR_INVALID, "cols[%u] is NULL", j);
     c->in_stage.ensure(N * n_cols);
     std::vector<std::pair<uint32_t, uint32_t>> chunks;
-    for (uint32_t c0 = 0, sz = 8; c0 < n_cols; c0 += sz, sz = std::min(sz + 8, 24u)) chunks.push_back({c0, std::min(sz, n_cols - c0)});
+    // 8, 16, 24, 24, ... columns; `doubling` (the caller also hashes each chunk, so compute per chunk dwarfs its copy): 8, 16, 32, 64, 64, ...
+    // — fewer, larger launches and fewer sponge-state hand-overs
+    for (uint32_t c0 = 0, sz = 8; c0 < n_cols; c0 += sz, sz = doubling ? std::min(2 * sz, 64u) : std::min(sz + 8, 24u))
+        chunks.push_back({c0, std::min(sz, n_cols - c0)});
     if (c->chunk_ev.size() < chunks.size()) {
         size_t old = c->chunk_ev.size();
         c->chunk_ev.resize(chunks.size(), nullptr);
@@ -656,14 +676,25 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
     memset(c->launches, 0, sizeof c->launches);
 
     record(c, GL_STAGE_H2D);
+    // Host columns with more than one chunk: the leaf sponge runs chunk by chunk behind the LDE of each chunk (leaf_absorb_kernel), so the
+    // PCIe copy of the later chunks hides behind hashing; the stage clock then books those launches under "lde" (they interleave with it).
+    const bool stream_hash = host_cols && c->stream_hash && n_cols > 8 && n_cols > 4;
+    bool leaves_hashed = false;
     if (host_cols) {
         if (!is_coeffs) c->vals.ensure(N * pitch);
+        if (stream_hash) c->hash_state.ensure(12 * R);
         for_each_host_chunk(c, host_cols, n_cols, N, [&](uint32_t c0, uint32_t nc, bool first) {
             const uint32_t width = std::min(round_up(nc, 8), pitch - c0);
             if (first) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); }   // h2d = first chunk
             lde_columns(c, c->in_stage.p + (uint64_t)c0 * N, N, c0, nc, width, log_n, rate_bits, is_coeffs, c->vals.p, t->coeffs.p, pitch,
                         t->leaves.p, pitch, 8, true, false);
-        });
+            if (stream_hash) {
+                const bool last = c0 + nc == n_cols;
+                leaf_absorb(c, t->leaves.p, R, n_cols, pitch, cap_height, c0, c0 + nc, c->hash_state.p, t->digests.p, t->d_cap.p, c0 == 0, last,
+                            &c->launches[GL_STAGE_LEAF_HASH]);
+                leaves_hashed = leaves_hashed || last;
+            }
+        }, stream_hash);
     } else {
         record(c, GL_STAGE_TRANSPOSE);
         lde_stage(c, d_cols_in, col_stride, n_cols, log_n, rate_bits, is_coeffs, t->coeffs.p, pitch, t->leaves.p, pitch, true);
@@ -681,8 +712,13 @@ int commit_impl(gl_ctx* c, const uint64_t* const* host_cols, const uint64_t* d_c
     }
     record(c, GL_STAGE_LEAF_HASH);
     if (early_copyback) CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));
-    merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
-                 &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    if (leaves_hashed) {
+        CUDA_CHECK(cudaEventRecord(c->ev[GL_STAGE_TREE], c->stream));
+        merkle_levels(c, R, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_TREE]);
+    } else {
+        merkle_build(c, t->leaves.p, R, n_cols, pitch, cap_height, t->digests.p, t->d_cap.p, &c->launches[GL_STAGE_LEAF_HASH],
+                     &c->launches[GL_STAGE_TREE], c->ev[GL_STAGE_TREE]);
+    }
     record(c, GL_STAGE_D2H);
     if (early_copyback) {
         // enqueued after the hash kernels were launched: with pageable host memory these calls block the host thread while they
@@ -779,6 +815,7 @@ int gl_ctx_create(gl_ctx** out, int device) {
     if (cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GL_ERR_CUDA; }
     if (const char* m = getenv("GL_SCATTER_MODE")) c->scatter_mode = atoi(m);
     if (const char* m = getenv("GL_TRACE")) c->trace = atoi(m) != 0;
+    if (const char* m = getenv("GL_STREAM_HASH")) c->stream_hash = atoi(m) != 0;
     if (const char* m = getenv("GL_NTT_VERSION")) c->ntt_version = atoi(m);
     if (const char* m = getenv("GL_NTT_G10")) c->ntt_g10 = atoi(m);
     if (const char* m = getenv("GL_NTT_MAX_A")) c->ntt_max_a = atoi(m);
@@ -803,7 +840,7 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->pass_roots.clear();
     c->lde_tables.clear();
     c->coset_cache.clear();
-    c->in_stage.release(); c->vals.release(); c->scratch.release();
+    c->in_stage.release(); c->vals.release(); c->scratch.release(); c->hash_state.release();
     DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);

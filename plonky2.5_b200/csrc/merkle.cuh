@@ -64,6 +64,51 @@ leaf_hash_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t l
     store_digest(dst, s);
 }
 
+// Streaming form of the leaf sponge: absorbs columns [col0, col1) of every leaf (col0 a multiple of the rate 8; col1 a multiple of 8 or the
+// leaf's end) and carries the 12-word sponge state in `state` ([12][n_leaves], one coalesced word per lane and leaf) between launches.
+// The overwrite-mode sponge consumes a row strictly left to right, so the column chunks of a host->device commit can be hashed as soon as
+// their LDE is done, while later chunks are still crossing PCIe: the copy hides behind the hashing instead of sitting in front of it.
+// first: start from the zero state; last: write the digest instead of the state.  Same permutations, same order => same digests.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, LEAF_MIN_BLOCKS)
+leaf_absorb_kernel(const uint64_t* __restrict__ leaves, uint32_t pitch, uint32_t leaf_len, uint32_t col0, uint32_t col1, uint64_t n_leaves,
+                   uint32_t log_sub, uint64_t* __restrict__ state, uint64_t* __restrict__ digests, uint64_t* __restrict__ cap, int first, int last) {
+    const uint64_t leaf = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (leaf >= n_leaves) return;
+    const uint64_t* row = leaves + leaf * pitch;
+    uint64_t s[poseidon::WIDTH];
+    // overwrite mode: a full 8-column group replaces lanes 0..7, so only the capacity lanes 8..11 have to travel between launches
+    // unless the group that follows the boundary is the leaf's short tail (which keeps the lanes it does not cover)
+    const bool in_full = leaf_len - col0 >= 8;
+#pragma unroll
+    for (int i = 0; i < poseidon::WIDTH; i++) s[i] = (first || (i < 8 && in_full)) ? 0 : state[(uint64_t)i * n_leaves + leaf];
+#pragma unroll 1
+    for (uint32_t k = col0; k < col1; k += 8) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(row + k);
+        ulonglong2 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+        uint64_t in[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
+        const uint32_t rem = leaf_len - k;   // >= 1
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((uint32_t)i < rem) s[i] = in[i];
+        poseidon::permute(s);
+    }
+    if (!last) {
+        const bool out_full = leaf_len - col1 >= 8;
+#pragma unroll
+        for (int i = 0; i < poseidon::WIDTH; i++)
+            if (i >= 8 || !out_full) state[(uint64_t)i * n_leaves + leaf] = s[i];
+        return;
+    }
+    uint64_t* dst;
+    if (log_sub == 0) dst = cap + 4 * leaf;
+    else {
+        uint64_t L = 1ULL << log_sub, t = leaf >> log_sub, j = leaf & (L - 1);
+        dst = digests + 4 * (t * 2 * (L - 1) + digest_index(0, j));
+    }
+    store_digest(dst, s);
+}
+
 // One thread per node of layer `layer` (1..log_sub): two_to_one(children).
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, LEAF_MIN_BLOCKS)

@@ -225,9 +225,9 @@ def test_stage_times_and_launch_counts(ctx):
     cols = splitmix_columns(5, 16, 1 << 10)
     g.PolynomialBatch.from_values(list(cols), 3, False, 4, ctx=ctx)
     ms, launches = ctx.stage_times()
-    # host columns arrive in chunks of 8, 16, 24, ... columns (copy/compute overlap): 16 columns = 2 chunks, each with its own
-    # iNTT (1 pass at N = 2^10) and 8 coset NTTs
-    assert launches["leaf_hash"] == 1 and launches["tree"] == 13 - 4 and launches["lde"] == 16 and launches["intt"] == 2
+    # host columns arrive in chunks of 8, 16, 32, ... columns (copy/compute overlap): 16 columns = 2 chunks, each with its own
+    # iNTT (1 pass at N = 2^10), 8 coset NTTs and one launch of the streaming leaf sponge over its columns
+    assert launches["leaf_hash"] == 2 and launches["tree"] == 13 - 4 and launches["lde"] == 16 and launches["intt"] == 2
     assert all(v >= 0 for v in ms.values())
 
 
