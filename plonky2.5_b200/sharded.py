@@ -77,6 +77,18 @@ class ShardPlan:
         return 8 * self.rows_per_rank * (self.world - 1) * max(self.col_counts)
 
 
+def coset_blocks_of_rank(plan: ShardPlan, rank: int) -> List[Tuple[int, int]]:
+    """Coset-sharded plan: the (leaf block, LDE coset) pairs rank `rank` evaluates.  Leaf rows are stored in bit-reversed LDE order, so leaf
+    block b (rows [b*N, (b+1)*N)) is exactly coset s = bitrev_r(b) — the points 7 * w_R^s * w_N^m — in the in-place-DIF order of m; a rank
+    owns 2^r / G consecutive blocks (its contiguous leaf range = whole cap subtrees)."""
+    n_cosets = 1 << plan.rate_bits
+    if plan.world > n_cosets:
+        raise ValueError("coset sharding needs world <= 2^rate_bits")
+    per = n_cosets // plan.world
+    rev = lambda b: int(format(b, "0%db" % plan.rate_bits)[::-1], 2) if plan.rate_bits else 0
+    return [(b, rev(b)) for b in range(rank * per, (rank + 1) * per)]
+
+
 def exchange_reference(plan: ShardPlan, shards: List[np.ndarray]) -> List[np.ndarray]:
     """Host model of step 2 for tests: shards[g] is rank g's [R][pitch_g] LDE output; returns each rank's [R/G][n_cols] leaves."""
     out = []

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import plonky25_b200 as g
-from plonky25_b200.sharded import ShardPlan, exchange_reference
+from plonky25_b200.sharded import ShardPlan, coset_blocks_of_rank, exchange_reference
 
 
 def test_plan_partitions_cover_everything():
@@ -102,3 +102,90 @@ def test_exchange_reference_model():
         r0, _ = plan.row_range(k)
         want = (np.arange(r0, r0 + plan.rows_per_rank, dtype=np.int64)[:, None] * 1000 + np.arange(37, dtype=np.int64)[None, :])
         assert np.array_equal(leaves[k], want)
+
+
+# ---- coset-sharded plan (the default multi-GPU plan): host logic on CPU, the exchange over gloo at world_size 2 -------------------------
+def _coset_leaves(oc, coeff_block, log_n, rate_bits, s):
+    """what gl_dev_lde_own_cosets computes for one coefficient block and one coset, with the oracle: rows m = in-place-DIF order of the
+    size-N NTT of coeffs * g_s^j, g_s = 7 * w_R^s"""
+    n = 1 << log_n
+    P = 0xFFFF_FFFF_0000_0001
+    w_R = pow(1753635133440165772, 1 << (32 - log_n - rate_bits), P)
+    g_s = 7 * pow(w_R, s, P) % P
+    rev = [int(format(i, "0%db" % log_n)[::-1], 2) if log_n else 0 for i in range(n)]
+    cols = []
+    for c in coeff_block:                                    # [n_cols][N]
+        vals = oc.coset_fft(c, g_s)                          # natural order
+        cols.append(vals[rev])
+    return np.stack(cols, axis=1)                            # [N][n_cols]
+
+
+def _coset_worker(rank, world, port, cols_shape, q):
+    import torch
+    import torch.distributed as dist
+    from oracle_c import OracleC, splitmix_columns
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_cols, log_n, r, h = cols_shape
+        oc = OracleC()
+        oc.set_threads(1)
+        plan = ShardPlan(n_cols, log_n, r, h, world)
+        x = splitmix_columns(321, n_cols, 1 << log_n)
+        c0, c1 = plan.col_range(rank)
+        my_coeffs = np.stack([oc.ifft(x[j]) for j in range(c0, c1)])                 # gl_dev_intt on this rank's column shard
+        # the exchange: every rank ends up with every coefficient block (the product pulls them over NVLink; here an all-gather of padded blocks)
+        width = max(plan.col_counts)
+        mine = torch.zeros((width, 1 << log_n), dtype=torch.int64)
+        mine[:c1 - c0] = torch.from_numpy(my_coeffs.view(np.int64))
+        allb = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        blocks = [b.numpy().view(np.uint64)[:plan.col_counts[g]] for g, b in enumerate(allb)]
+        # own cosets of every block -> own leaf range
+        rows = []
+        for (_, s) in coset_blocks_of_rank(plan, rank):
+            rows.append(np.concatenate([_coset_leaves(oc, blocks[g], log_n, r, s) for g in range(world)], axis=1))
+        leaves = np.concatenate(rows, axis=0)
+        ref = oc.commit(x, r, h)
+        r0, r1 = plan.row_range(rank)
+        ok = bool(np.array_equal(leaves, ref["leaves"][r0:r1]))
+        dig, cap = oc.merkle_new(leaves, plan.local_cap_height)
+        per = (1 << h) // world
+        ok = ok and bool(np.array_equal(cap, ref["cap"][rank * per:(rank + 1) * per]))
+        ok = ok and bool(np.array_equal(dig, ref["digests"][rank * plan.digests_per_rank():(rank + 1) * plan.digests_per_rank()]))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_coset_blocks_partition_the_leaf_rows():
+    for (cols, log_n, r, h, world) in [(135, 20, 3, 4, 8), (135, 16, 3, 4, 2), (20, 6, 2, 2, 4), (9, 5, 1, 1, 2), (7, 4, 0, 0, 1)]:
+        p = ShardPlan(cols, log_n, r, h, world)
+        seen = []
+        for k in range(world):
+            blocks = coset_blocks_of_rank(p, k)
+            assert [b for b, _ in blocks] == list(range(k * len(blocks), (k + 1) * len(blocks)))      # contiguous leaf range
+            assert len(blocks) * (1 << log_n) == p.rows_per_rank
+            seen += [s for _, s in blocks]
+        assert sorted(seen) == list(range(1 << r))                                                  # every coset exactly once
+    with pytest.raises(ValueError):
+        coset_blocks_of_rank(ShardPlan(64, 6, 1, 3, 4), 0)                                          # 4 ranks > 2 cosets
+
+
+@pytest.mark.parametrize("shape", [(19, 5, 2, 2), (135, 4, 1, 1)])
+def test_coset_plan_over_gloo_world2(shape):
+    """two ranks, gloo: iNTT of the column shard -> exchange of coefficient blocks -> own cosets of all columns -> own subtrees: each
+    rank's leaf range, digest slice and cap slice equal the single commit's (the oracle stands in for the kernels)"""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_coset_worker, args=(k, 2, port, shape, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
