@@ -4,6 +4,7 @@
 // MerkleTree::new and fri/prover.rs · fri_committed_trees (driven from /root/reference/src/p3/mod.rs:250,260).
 // Everything here is plumbing around the kernels in ntt.cuh / merkle.cuh / fri.cuh; there is no CPU compute path.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler injects the NVTX library
 
 #include <cstdio>
 #include <algorithm>
@@ -36,6 +37,17 @@ struct GlError {
     int code;
     std::string msg;
 };
+
+// NVTX ranges named after plonky2's own TimingTree labels (fri/oracle.rs · from_values / from_coeffs: "IFFT", "FFT + blinding",
+// "transpose LDEs", "build Merkle tree"; fri/prover.rs: "fold codewords in the commitment phase", "find proof-of-work witness"), so a
+// timeline of the drop-in reads like upstream's `timing` output.  Host-side ranges around the enqueue of each stage.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 
 #define GL_THROW(code, ...)                              \
     do {                                                 \
@@ -472,6 +484,7 @@ void merkle_levels(gl_ctx* c, uint64_t n_leaves, uint32_t cap_height, uint64_t* 
 void merkle_build(gl_ctx* c, const uint64_t* d_leaves, uint64_t n_leaves, uint32_t leaf_len, uint32_t pitch,
                   uint32_t cap_height, uint64_t* d_digests, uint64_t* d_cap, uint32_t* leaf_launches,
                   uint32_t* tree_launches, cudaEvent_t after_leaves) {
+    NvtxRange nv("build Merkle tree");
     uint32_t log_leaves = log2_exact(n_leaves);
     uint32_t log_sub = log_leaves - cap_height;
     constexpr int LB = LEAF_BLOCK;
@@ -520,6 +533,7 @@ Fri* find_fri(gl_ctx* c, gl_handle h) {
 
 void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream)); }
 
+
 // iNTT + coset LDE of `n_cols` device columns (column-major, col_stride apart) into columns [col0, col0 + padded) of the
 // row-major outputs.  Column groups are independent, so a batch can be processed in chunks (pipelined behind the
 // host->device copies in gl_commit).  col0 must be a multiple of 8.
@@ -529,6 +543,8 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
                  uint32_t first_coset = 0) {
     const uint64_t N = 1ULL << log_n;
     const uint32_t cols_padded = round_up(n_cols, G);
+    NvtxRange nv_lde(is_coeffs ? "FFT + blinding (coset LDE, leaves stored bit-reversed: includes 'transpose LDEs')"
+                               : "IFFT, FFT + blinding (coset LDE, leaves stored bit-reversed: includes 'transpose LDEs')");
     dim3 tb(32, 8);
     dim3 tg((uint32_t)((N + 31) / 32), (width + 31) / 32);
     uint32_t* l_tr = timed ? &c->launches[GL_STAGE_TRANSPOSE] : nullptr;
@@ -1627,6 +1643,7 @@ int gl_fri_fold(gl_ctx* c, gl_handle fh, const uint64_t beta[2]) {
     Fri* f = find_fri(c, fh);
     if (!beta) GL_THROW(GL_ERR_INVALID, "beta is NULL");
     if (f->last_arity_bits == 0) GL_THROW(GL_ERR_INVALID, "gl_fri_fold without a preceding gl_fri_commit_layer");
+    NvtxRange nv("fold codewords in the commitment phase");
     const uint32_t arity_bits = f->last_arity_bits;   // upstream folds by the arity of the layer it just committed
     f->last_arity_bits = 0;
     uint64_t arity = 1ULL << arity_bits;
@@ -2136,6 +2153,7 @@ int gl_fri_pow(gl_ctx* c, const uint64_t sponge_state[12], const uint64_t* input
                uint64_t* out_witness) {
     GL_API_BEGIN(c)
     if (!sponge_state || !out_witness || (n_inputs && !input_buffer)) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    NvtxRange nv("find proof-of-work witness");
     if (n_inputs >= 8) GL_THROW(GL_ERR_INVALID, "input buffer must hold fewer than SPONGE_RATE = 8 elements");
     if (min_leading_zeros > 40) GL_THROW(GL_ERR_UNSUPPORTED, "min_leading_zeros = %u: search space too large", min_leading_zeros);
     uint64_t st[12];
