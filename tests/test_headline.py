@@ -86,3 +86,26 @@ def test_headline_device_path_matches_golden(ctx, name):
         assert np.array_equal(cap, np.array(gold["cap"], dtype=np.uint64))
     finally:
         lib.gl_dev_free(ctx.handle, d)
+
+
+def test_large_degree_narrow_batch_matches_oracle(ctx, oc):
+    """the largest degree the suite runs: 2^24 x 5 columns, rate_bits 1 — the three-pass 8+8+8 NTT plan, 2^25 leaf rows, and 2^24 x 2
+    with leaves of <= 4 elements (hash_or_noop copies them, no permutation) — against the oracle run live (narrow, so it takes seconds)"""
+    import plonky25_b200 as g
+    if _free_host_bytes() < 24 << 30:
+        pytest.skip("not enough host memory")
+    for (log_n, n_cols, r, h) in [(24, 5, 1, 4), (24, 2, 1, 0)]:
+        n = 1 << log_n
+        cols = splitmix_columns(900 + n_cols, n_cols, n)
+        ref = oc.commit(cols, r, h, want=("digests",))
+        pb = g.PolynomialBatch.from_values(list(cols), r, False, h, ctx=ctx)
+        t = pb.merkle_tree
+        try:
+            assert np.array_equal(t.cap.hashes, ref["cap"])
+            assert headline.sha(t.digests) == headline.sha(ref["digests"])
+            t._digests = None
+            rows, sib = t.open_batch([0, 1, (n << r) - 1, 12345678])
+            for q, i in enumerate([0, 1, (n << r) - 1, 12345678]):
+                assert oc.verify_path(rows[q], i, sib[q], ref["cap"])
+        finally:
+            t.free()
