@@ -255,6 +255,9 @@ int gl_lde_scatter(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, ui
  * The caller synchronises the ranks between the two calls (every block complete) — see plonky2.5_b200/sharded.py.                   */
 int gl_dev_intt(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n, int input_is_coeffs,
                 uint64_t* d_out_coeffs, uint32_t coeff_pitch);
+/* gl_dev_intt with HOST columns (cols[j] = N words): chunked host->device copies overlapped with the transposes / iNTTs of the previous chunk */
+int gl_intt_host(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, int input_is_coeffs, uint64_t* d_out_coeffs,
+                 uint32_t coeff_pitch);
 int gl_dev_lde_own_cosets(gl_ctx* ctx, uint64_t* const* peer_coeffs, uint64_t* const* d_stage, const uint32_t* pitches,
                           const uint32_t* col_counts, const uint32_t* col_offsets, uint32_t n_peers, uint32_t self, uint32_t log_n,
                           uint32_t rate_bits, uint64_t* d_leaves, uint32_t leaf_pitch);

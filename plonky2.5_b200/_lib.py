@@ -78,6 +78,7 @@ SIGNATURES = {
     "gl_lde_scatter": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_uint32, c_int, POINTER(c_void_p), c_uint32,
                                c_uint32, c_uint32, c_void_p, c_uint32, c_uint32]),
     "gl_dev_intt": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int, c_void_p, c_uint32]),
+    "gl_intt_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_int, c_void_p, c_uint32]),
     "gl_dev_lde_own_cosets": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32),
                                       c_uint32, c_uint32, c_uint32, c_uint32, c_void_p, c_uint32]),
     "gl_dev_ipc_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), c_void_p]),

@@ -540,7 +540,7 @@ void record(gl_ctx* c, int i) { CUDA_CHECK(cudaEventRecord(c->ev[i], c->stream))
 void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t col0, uint32_t n_cols, uint32_t width,
                  uint32_t log_n, uint32_t rate_bits, int is_coeffs, uint64_t* d_vals, uint64_t* d_coeffs, uint32_t coeff_pitch,
                  uint64_t* d_rows, uint32_t row_pitch, int G, bool timed, bool split_events, const ntt::Scatter* scatter = nullptr,
-                 uint32_t first_coset = 0) {
+                 uint32_t first_coset = 0, bool intt_only = false) {
     const uint64_t N = 1ULL << log_n;
     const uint32_t cols_padded = round_up(n_cols, G);
     NvtxRange nv_lde(is_coeffs ? "FFT + blinding (coset LDE, leaves stored bit-reversed: includes 'transpose LDEs')"
@@ -564,6 +564,7 @@ void lde_columns(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_
         run_ntt(c, d_vals + col0, coeff_pitch, coeffs, coeff_pitch, cols_padded, log_n, true, nullptr, G, l_in);
     }
     if (split_events) record(c, GL_STAGE_LDE);
+    if (intt_only) return;                        // coset-sharded plan: the LDE runs after the coefficient exchange
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
     for (uint32_t k = 0; k < (1u << rate_bits); k++) {
         const uint32_t s = (k + first_coset) & ((1u << rate_bits) - 1);
@@ -1038,6 +1039,33 @@ int gl_dev_intt(gl_ctx* c, const uint64_t* d_cols, uint64_t col_stride, uint32_t
     record(c, GL_STAGE_LDE);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int i : {GL_STAGE_TRANSPOSE, GL_STAGE_INTT}) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
+int gl_intt_host(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, int input_is_coeffs, uint64_t* d_out_coeffs,
+                 uint32_t coeff_pitch) {
+    GL_API_BEGIN(c)
+    check_shape(n_cols, log_n, 0, 0);
+    if (!cols || !d_out_coeffs) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (coeff_pitch % 4 || coeff_pitch < n_cols) GL_THROW(GL_ERR_INVALID, "coeff_pitch must be a multiple of 4 and >= n_cols");
+    const int G = (round_up(n_cols, 8) - n_cols >= 4) ? 4 : 8;
+    if (coeff_pitch < round_up(n_cols, (uint32_t)G)) GL_THROW(GL_ERR_INVALID, "coeff_pitch too small for the padded column group");
+    const uint64_t N = 1ULL << log_n;
+    get_roots(c, log_n);
+    if (!input_is_coeffs) c->vals.ensure(N * coeff_pitch);
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT, GL_STAGE_LDE}) { c->launches[i] = 0; c->stage_ms[i] = 0; }
+    record(c, GL_STAGE_H2D);
+    // the shard crosses PCIe in chunks; transpose + iNTT of chunk k run while chunk k+1 is on the wire
+    for_each_host_chunk(c, cols, n_cols, N, [&](uint32_t c0, uint32_t nc, bool first) {
+        const uint32_t width = std::min(round_up(nc, (uint32_t)G), coeff_pitch - c0);
+        if (first) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); }
+        lde_columns(c, c->in_stage.p + (uint64_t)c0 * N, N, c0, nc, width, log_n, 0, input_is_coeffs, c->vals.p, d_out_coeffs, coeff_pitch, nullptr, 0, G,
+                    true, false, nullptr, 0, true);
+    });
+    record(c, GL_STAGE_LDE);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i : {GL_STAGE_H2D, GL_STAGE_TRANSPOSE, GL_STAGE_INTT}) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     return GL_OK;
     GL_API_END(c)
 }

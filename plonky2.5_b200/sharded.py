@@ -241,12 +241,7 @@ class ShardedCommit:
             # its block before all peers have pulled it: the next commit starts after the cap all-gather, which a rank enters only after
             # its own hashing, i.e. after its pulls.
             self._check(lib.gl_dev_intt(h, d_cols.data_ptr(), n, ncg, p.log_n, 0, self._coeff_ptr, p.pitches[self.rank]))
-            self._intt_ms = self.ctx.stage_times()[0]
-            with torch.cuda.stream(self._stream):
-                self.dist.all_reduce(self._flag)
-            self._check(lib.gl_dev_lde_own_cosets(h, self._peer_coeffs, self._stage_ptrs, self._pitches, self._counts, self._offsets, p.world,
-                                                  self.rank, p.log_n, p.rate_bits, self.leaves_ptr, p.leaf_pitch))
-            return self._hash()
+            return self._coset_tail()
         if self.exchange == "p2p":
             # Nobody may write into a leaf buffer its owner is still hashing: the previous commit ended with the cap
             # all-gather, which no rank enters before its own hashing is done, and every rank read its result — so all
@@ -280,6 +275,15 @@ class ShardedCommit:
             off += p.rows_per_rank * p.pitches[q]
         return self._hash()
 
+    def _coset_tail(self) -> np.ndarray:
+        """coset plan after the own coefficient block is complete: barrier, pull + own cosets, hash, cap gather"""
+        p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
+        with torch.cuda.stream(self._stream):
+            self.dist.all_reduce(self._flag)
+        self._check(lib.gl_dev_lde_own_cosets(h, self._peer_coeffs, self._stage_ptrs, self._pitches, self._counts, self._offsets, p.world,
+                                              self.rank, p.log_n, p.rate_bits, self.leaves_ptr, p.leaf_pitch))
+        return self._hash()
+
     def commit_host(self, h_cols) -> np.ndarray:
         """The same commit from HOST columns: h_cols = this rank's [n_cols_g][N] tensor in (ideally pinned) host memory.  In the
         fused mode the shard crosses PCIe in chunks behind the NTTs of the previous chunk (gl_lde_scatter)."""
@@ -290,18 +294,19 @@ class ShardedCommit:
         if self.exchange == "coset" and self._auto:
             # HOST columns: in the coset plan nothing can start before every rank's whole shard has crossed PCIe and gone through the
             # iNTT, whereas the column->row plan hides the copy behind the LDE NTTs chunk by chunk (gl_lde_scatter) — so with
-            # exchange="auto" host inputs take that plan (its buffers are created on first use and kept)
+            # exchange="auto" host inputs take that plan (its buffers are created on first use and kept).  Measured at 8 GPUs: the two are
+            # equal there (21.2 vs 21.5 ms per commit) because eight concurrent host->device copies share the host's PCIe/memory path
+            # (~20 GB/s per GPU instead of ~50), so the shard's copy is as long as the whole LDE stage either way
             if self._host_impl is None:
                 self._host_impl = ShardedCommit(self.ctx, self.plan, self.rank, self.dist, self.torch, exchange="p2p")
             out = self._host_impl.commit_host(h_cols)
             self.digests = self._host_impl.digests
             return out
         if self.exchange == "coset":
-            if getattr(self, "_h2d", None) is None:
-                self._h2d = torch.empty((ncg, n), dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
-            self._h2d.copy_(h_cols, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return self.commit(self._h2d)
+            base = h_cols.data_ptr()
+            ptrs = (ctypes.c_void_p * ncg)(*[base + 8 * n * j for j in range(ncg)])
+            self._check(lib.gl_intt_host(h, ptrs, ncg, p.log_n, 0, self._coeff_ptr, p.pitches[self.rank]))   # chunked H2D behind the iNTTs
+            return self._coset_tail()
         if self.exchange != "p2p":
             d = h_cols.to(torch.device("cuda", self.ctx.device), non_blocking=True)
             torch.cuda.current_stream().synchronize()
