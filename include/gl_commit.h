@@ -177,6 +177,14 @@ int gl_gate_eval_rows(gl_ctx* ctx, int kind, uint32_t param, const uint64_t* row
 int gl_quotient_begin(gl_ctx* ctx, gl_handle wires_batch, uint32_t n_challenges, gl_handle* out_quotient);
 int gl_quotient_add_gate(gl_ctx* ctx, gl_handle quotient, int kind, uint32_t param, const uint64_t* alphas, uint32_t constraint_offset,
                          gl_handle filter_batch, uint32_t filter_col);
+/* the permutation-argument terms of eval_vanishing_poly_base_batch (plonk/vanishing_poly.rs; restated, parity unpinned): for every challenge i
+ * L_0(x)(Z_i(x) - 1), then check_partial_products of every challenge — vanishing_terms[0 .. n_ch*(1 + n_chunks)), each alpha_k reducing the
+ * whole list; gate constraints follow from constraint_offset = n_ch * (1 + n_chunks).  sigmas_batch: the constants+sigmas commit, the sigma
+ * polynomials at columns [sigma_col0, sigma_col0 + n_routed); zs_batch: the commit of gl_partial_products' columns (Z first); all three
+ * batches share the wires batch's degree and rate_bits.                                                                                 */
+int gl_quotient_add_permutation(gl_ctx* ctx, gl_handle quotient, gl_handle sigmas_batch, uint32_t sigma_col0, gl_handle zs_batch,
+                                uint32_t n_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas, const uint64_t* gammas,
+                                const uint64_t* alphas);
 int gl_quotient_read(gl_ctx* ctx, gl_handle quotient, uint64_t* out);
 /* the tail of compute_quotient_polys and the quotient commit of prove() (plonky2 plonk/prover.rs), without leaving the device:
  * acc_k / Z_H on the coset (ZeroPolyOnCoset::eval_inverse), coset_ifft(7) to coefficients (degree < 2^rate_bits * N), split into

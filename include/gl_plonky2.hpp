@@ -685,6 +685,14 @@ public:
     /* acc[k][row] += filter(row) * sum_i alphas[k]^(constraint_offset + i) * constraint_i(row) */
     void add_gate(int kind, uint32_t param, const std::vector<F>& alphas, size_t constraint_offset = 0, const PolynomialBatch* filter_batch = nullptr,
                   size_t filter_col = 0);
+    /* the permutation-argument terms of eval_vanishing_poly_base_batch (vanishing_terms[0 .. n_ch * (1 + n_chunks))) */
+    void add_permutation(const PolynomialBatch& sigmas, size_t sigma_col0, const PolynomialBatch& zs_partial_products, size_t n_routed, size_t degree,
+                         const std::vector<F>& k_is, const std::vector<F>& betas, const std::vector<F>& gammas, const std::vector<F>& alphas) {
+        if (k_is.size() != n_routed || betas.size() != n_challenges_ || gammas.size() != n_challenges_ || alphas.size() != n_challenges_)
+            throw Panic("QuotientAccumulator::add_permutation: k_is per routed wire; betas / gammas / alphas per challenge");
+        ctx_->check(gl_quotient_add_permutation(ctx_->raw(), h_, sigmas.merkle_tree.handle(), uint32_t(sigma_col0), zs_partial_products.merkle_tree.handle(),
+                                                uint32_t(n_routed), uint32_t(degree), k_is.data(), betas.data(), gammas.data(), alphas.data()));
+    }
     std::vector<F> values() const {                       /* [num_challenges][R], row order = the leaves' */
         std::vector<F> out(n_challenges_ * n_rows_);
         ctx_->check(gl_quotient_read(ctx_->raw(), h_, out.data()));

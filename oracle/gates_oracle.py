@@ -501,3 +501,29 @@ def comparison_witness(a, b, num_bits, num_chunks, num_wires=135):
         w[4 + 5 * num_chunks + k] = (v >> k) & 1
     w[2] = w[4 + 5 * num_chunks + chunk_bits]
     return w
+
+
+def vanishing_permutation_terms(wires_row, sigmas_row, zs_row, zs_next_row, x, k_is, betas, gammas, degree, log_n):
+    """plonky2 plonk/vanishing_poly.rs · eval_vanishing_poly (the permutation-argument part; restated, upstream source absent): at a point x
+    with the routed wire values, the sigma values, the Z / partial-product values at x (columns: Z of every challenge, then each challenge's
+    partial products) and at g*x.  Returns vanishing_terms[0 .. n_ch*(1 + n_chunks)): the L_0(x)(Z_i - 1) terms, then check_partial_products
+    of every challenge."""
+    n = 1 << log_n
+    n_routed, n_ch = len(wires_row), len(betas)
+    n_chunks = -(-n_routed // degree)
+    n_pp = n_chunks - 1
+    l0 = (pow(x, n, P) - 1) * pow(n * (x - 1) % P, P - 2, P) % P
+    z1, pp_terms = [], []
+    for i in range(n_ch):
+        z_x, z_gx = zs_row[i], zs_next_row[i]
+        z1.append(l0 * (z_x - 1) % P)
+        nums = [(wires_row[j] + betas[i] * k_is[j] % P * x + gammas[i]) % P for j in range(n_routed)]
+        dens = [(wires_row[j] + betas[i] * sigmas_row[j] + gammas[i]) % P for j in range(n_routed)]
+        accs = [z_x] + [zs_row[n_ch + i * n_pp + c] for c in range(n_pp)] + [z_gx]
+        for c in range(n_chunks):
+            pn = pd = 1
+            for j in range(c * degree, min((c + 1) * degree, n_routed)):
+                pn = pn * nums[j] % P
+                pd = pd * dens[j] % P
+            pp_terms.append((accs[c] * pn - accs[c + 1] * pd) % P)
+    return z1 + pp_terms

@@ -576,6 +576,21 @@ class Quotient:
         self.ctx.lib.gl_ctx_aux_ms(self.ctx.handle, byref(ms))
         return float(ms.value)
 
+    def add_permutation(self, sigmas: "PolynomialBatch", sigma_col0: int, zs_partial_products: "PolynomialBatch", n_routed: int, degree: int,
+                        k_is, betas, gammas, alphas) -> float:
+        """the permutation-argument terms of eval_vanishing_poly_base_batch — L_0(x)(Z_i(x) - 1) for every challenge, then
+        check_partial_products of every challenge: vanishing_terms[0 .. n_ch * (1 + n_chunks)); gates follow from that offset.
+        `sigmas`: the constants+sigmas commit (sigma polynomials at columns [sigma_col0, sigma_col0 + n_routed));
+        `zs_partial_products`: the commit of partial_products_and_zs' columns.  Returns the kernel time in ms."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1) for a in (k_is, betas, gammas, alphas)]
+        if arrs[0].size != n_routed or any(a.size != self.n_challenges for a in arrs[1:]):
+            raise ValueError("k_is: one per routed wire; betas / gammas / alphas: one per challenge")
+        _check(self.ctx, self.ctx.lib.gl_quotient_add_permutation(self.ctx.handle, self._h, sigmas.merkle_tree._h, sigma_col0,
+                                                                  zs_partial_products.merkle_tree._h, n_routed, degree, *[_ptr(a) for a in arrs]))
+        ms = ctypes.c_float()
+        self.ctx.lib.gl_ctx_aux_ms(self.ctx.handle, byref(ms))
+        return float(ms.value)
+
     def values(self) -> np.ndarray:
         """[n_challenges][R] accumulated values, row order = the leaves' (row i = LDE point bitrev(i))"""
         out = np.zeros((self.n_challenges, self.wires.merkle_tree.n_leaves), dtype=np.uint64)

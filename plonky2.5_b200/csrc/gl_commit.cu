@@ -1982,6 +1982,67 @@ int gl_quotient_add_gate(gl_ctx* c, gl_handle qh, int kind, uint32_t param, cons
     GL_API_END(c)
 }
 
+int gl_quotient_add_permutation(gl_ctx* c, gl_handle qh, gl_handle sigmas_batch, uint32_t sigma_col0, gl_handle zs_batch, uint32_t n_routed,
+                                uint32_t degree, const uint64_t* k_is, const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas) {
+    GL_API_BEGIN(c)
+    Quotient* q = find_quotient(c, qh);
+    if (!k_is || !betas || !gammas || !alphas) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_routed == 0 || degree == 0) GL_THROW(GL_ERR_INVALID, "n_routed and degree must be positive");
+    Tree* tw = find_tree(c, q->wires);
+    Tree* ts = find_tree(c, sigmas_batch);
+    Tree* tz = find_tree(c, zs_batch);
+    const uint32_t n_ch = q->n_challenges, n_chunks = (n_routed + degree - 1) / degree, n_terms = n_ch * (1 + n_chunks);
+    if (!tw->has_coeffs || tw->rate_bits > 6) GL_THROW(GL_ERR_UNSUPPORTED, "the wires batch must be a PolynomialBatch commit with rate_bits <= 6");
+    for (Tree* t : {ts, tz})
+        if (t->n_leaves != tw->n_leaves || t->degree_log != tw->degree_log || t->rate_bits != tw->rate_bits)
+            GL_THROW(GL_ERR_INVALID, "Polynomial degrees inconsistent (the sigma / Z batches must share the wires batch's degree and rate_bits)");
+    if (tw->leaf_len < n_routed) GL_THROW(GL_ERR_INVALID, "the wires batch has %u columns, %u routed wires requested", tw->leaf_len, n_routed);
+    if (sigma_col0 + n_routed > ts->leaf_len) GL_THROW(GL_ERR_INVALID, "sigma columns [%u, %u) out of range", sigma_col0, sigma_col0 + n_routed);
+    if (tz->leaf_len != n_ch * n_chunks) GL_THROW(GL_ERR_INVALID, "the Z / partial-products batch must have n_challenges * ceil(n_routed / degree) = %u columns", n_ch * n_chunks);
+    if (n_terms > (uint32_t)gates::MAX_CONSTRAINTS) GL_THROW(GL_ERR_UNSUPPORTED, "too many permutation terms");
+    const uint32_t log_n = tw->degree_log, r = tw->rate_bits, bits = log_n + r;
+    perm::VanishArgs a{};
+    a.wires = tw->leaves.p; a.wires_pitch = tw->pitch;
+    a.sigmas = ts->leaves.p; a.sigmas_pitch = ts->pitch; a.sigma_col0 = sigma_col0;
+    a.zs = tz->leaves.p; a.zs_pitch = tz->pitch;
+    a.W = get_roots(c, bits);
+    a.acc = q->acc.p;
+    a.log_n = log_n; a.rate_bits = r; a.n_routed = n_routed; a.degree = degree; a.n_chunks = n_chunks; a.n_ch = n_ch;
+    a.n_inv = gl::h_inv(((uint64_t)1 << log_n) % gl::P);
+    {
+        const uint64_t gN = gl::h_pow(gl::COSET_SHIFT, 1ULL << log_n), wr = gl::h_root_of_unity(r);
+        uint64_t cur = gN;
+        for (uint32_t j = 0; j < (1u << r); j++) { a.zh[j] = cur - 1; cur = gl::h_mul(cur, wr); }
+    }
+    std::vector<uint64_t> host(n_routed + (size_t)n_ch * n_terms);
+    for (uint32_t j = 0; j < n_routed; j++) host[j] = gl::canon(k_is[j]);
+    for (uint32_t k = 0; k < n_ch; k++) {
+        a.beta[k] = gl::canon(betas[k]); a.gamma[k] = gl::canon(gammas[k]);
+        const uint64_t al = gl::canon(alphas[k]);
+        uint64_t cur = 1;
+        for (uint32_t t = 0; t < n_terms; t++) { host[n_routed + (size_t)k * n_terms + t] = cur; cur = gl::h_mul(cur, al); }
+    }
+    c->scratch.ensure(host.size());
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    a.k_is = c->scratch.p;
+    a.powers = c->scratch.p + n_routed;
+    const uint32_t grid = (uint32_t)((q->n_rows + 127) / 128);
+    const size_t smem = (size_t)n_ch * n_terms * 8;
+    CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+    switch (n_ch) {
+        case 1: perm::vanishing_perm_kernel<1><<<grid, 128, smem, c->stream>>>(a); break;
+        case 2: perm::vanishing_perm_kernel<2><<<grid, 128, smem, c->stream>>>(a); break;
+        case 3: perm::vanishing_perm_kernel<3><<<grid, 128, smem, c->stream>>>(a); break;
+        default: perm::vanishing_perm_kernel<4><<<grid, 128, smem, c->stream>>>(a); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, c->ev[0], c->ev[1]));
+    return GL_OK;
+    GL_API_END(c)
+}
+
 int gl_quotient_read(gl_ctx* c, gl_handle qh, uint64_t* out) {
     GL_API_BEGIN(c)
     Quotient* q = find_quotient(c, qh);

@@ -109,4 +109,81 @@ __global__ void __launch_bounds__(1024) running_product_kernel(const Args a) {
     }
 }
 
+// The permutation-argument terms of plonky2 plonk/vanishing_poly.rs · eval_vanishing_poly_base_batch (restated; upstream source absent),
+// evaluated at every LDE row and folded into the quotient accumulator with the challenges' alpha powers.  vanishing_terms is ordered
+//     [ L_0(x) (Z_i(x) - 1)  for every challenge i ]  ++  [ check_partial_products of challenge 0, of challenge 1, ... ]  ++  gate constraints
+// and EVERY alpha_k reduces the whole list (reduce_with_powers), so term t contributes alpha_k^t * term_t to acc[k].
+// check_partial_products: with product_accs = [Z_i(x), pp_i0, .., pp_i(m-2), Z_i(g x)], chunk c gives
+//     accs[c] * prod_{j in chunk c} (w_j + beta_i k_j x + gamma_i)  -  accs[c+1] * prod_{j in chunk c} (w_j + beta_i sigma_j(x) + gamma_i).
+// Rows are leaf rows (row = LDE point index bitrev(row)); Z_i(g x) is the row of LDE point index + 2^rate_bits.
+struct VanishArgs {
+    const uint64_t* wires;  uint32_t wires_pitch;       // [R][pitch]: routed wires are columns [0, n_routed)
+    const uint64_t* sigmas; uint32_t sigmas_pitch, sigma_col0;
+    const uint64_t* zs;     uint32_t zs_pitch;          // columns: Z_0..Z_{n_ch-1}, then (n_chunks-1) partial products per challenge
+    const uint64_t* k_is;                               // [n_routed]
+    const uint64_t* W;                                  // w_R^e, e < R/2
+    const uint64_t* powers;                             // [n_ch][n_terms]: alpha_k^t
+    uint64_t* acc;                                      // [n_ch][R]
+    uint64_t beta[4], gamma[4], zh[64], n_inv;          // zh[s] = (7 w_R^s)^N - 1, s < 2^rate_bits
+    uint32_t log_n, rate_bits, n_routed, degree, n_chunks, n_ch;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(128) vanishing_perm_kernel(const VanishArgs a) {
+    extern __shared__ uint64_t pw[];   // [NCH][n_terms]
+    const uint32_t n_terms = NCH * (1 + a.n_chunks);
+    for (uint32_t i = threadIdx.x; i < NCH * n_terms; i += blockDim.x) pw[i] = a.powers[i];
+    __syncthreads();
+    const uint32_t bits = a.log_n + a.rate_bits;
+    const uint64_t R = 1ULL << bits, row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    const uint32_t idx = gl::bitrev32((uint32_t)row, bits);                       // LDE point index
+    const uint32_t idx_next = (idx + (1u << a.rate_bits)) & (uint32_t)(R - 1);
+    const uint64_t row_next = gl::bitrev32(idx_next, bits);
+    // x = 7 * w_R^idx
+    const uint32_t half = (uint32_t)(R >> 1);
+    const uint64_t wr = idx >= half ? gl::P - a.W[idx - half] : a.W[idx];
+    const uint64_t x = gl::mulc(wr, gl::COSET_SHIFT);
+    // L_0(x) = (x^N - 1) / (N (x - 1))
+    const uint64_t zh = a.zh[idx & ((1u << a.rate_bits) - 1)];
+    const uint64_t l0 = gl::mulc(gl::mulc(zh, a.n_inv), inverse(gl::sub(x, 1)));
+    const uint64_t* w = a.wires + row * a.wires_pitch;
+    const uint64_t* s = a.sigmas + row * a.sigmas_pitch + a.sigma_col0;
+    const uint64_t* z = a.zs + row * a.zs_pitch;
+    const uint64_t* zn = a.zs + row_next * a.zs_pitch;
+    uint64_t acc[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; k++) acc[k] = 0;
+    auto emit = [&](uint32_t t, uint64_t v) {
+#pragma unroll
+        for (int k = 0; k < NCH; k++) acc[k] = gl::add(acc[k], gl::mulc(v, pw[k * n_terms + t]));
+    };
+    const uint32_t n_pp = a.n_chunks - 1;
+#pragma unroll 1
+    for (uint32_t i = 0; i < (uint32_t)NCH; i++) {
+        const uint64_t z_x = gl::canon(z[i]), z_gx = gl::canon(zn[i]);
+        emit(i, gl::mulc(l0, gl::sub(z_x, 1)));
+        const uint64_t bx = gl::mulc(a.beta[i], x);
+        uint64_t prev = z_x;
+#pragma unroll 1
+        for (uint32_t c = 0; c < a.n_chunks; c++) {
+            uint64_t pn = 1, pd = 1;
+            const uint32_t j1 = min((c + 1) * a.degree, a.n_routed);
+            for (uint32_t j = c * a.degree; j < j1; j++) {
+                const uint64_t wv = gl::canon(w[j]);
+                pn = gl::mulc(pn, gl::add(gl::add(wv, gl::mulc(bx, a.k_is[j])), a.gamma[i]));
+                pd = gl::mulc(pd, gl::add(gl::add(wv, gl::mulc(a.beta[i], gl::canon(s[j]))), a.gamma[i]));
+            }
+            const uint64_t next = c + 1 < a.n_chunks ? gl::canon(z[NCH + i * n_pp + c]) : z_gx;
+            emit(NCH + i * a.n_chunks + c, gl::sub(gl::mulc(prev, pn), gl::mulc(next, pd)));
+            prev = next;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; k++) {
+        uint64_t* dst = a.acc + (uint64_t)k * R + row;
+        *dst = gl::add(*dst, acc[k]);
+    }
+}
+
 }  // namespace perm

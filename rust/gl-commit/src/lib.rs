@@ -472,6 +472,17 @@ impl<'c> Quotient<'c> {
         self.ctx.check(unsafe { ffi::gl_quotient_add_gate(self.ctx.raw, self.handle, kind as c_int, param, alphas.as_ptr(), constraint_offset as u32, fb, fc) })
     }
 
+    /// the permutation-argument terms of `eval_vanishing_poly_base_batch` (`vanishing_terms[0 .. n_ch * (1 + n_chunks))`)
+    #[allow(clippy::too_many_arguments)]
+    pub fn add_permutation(&mut self, sigmas: &DeviceTree<'c>, sigma_col0: usize, zs_partial_products: &DeviceTree<'c>, n_routed: usize, degree: usize,
+                           k_is: &[u64], betas: &[u64], gammas: &[u64], alphas: &[u64]) -> Result<(), Error> {
+        assert!(k_is.len() == n_routed && betas.len() == self.num_challenges && gammas.len() == self.num_challenges && alphas.len() == self.num_challenges);
+        self.ctx.check(unsafe {
+            ffi::gl_quotient_add_permutation(self.ctx.raw, self.handle, sigmas.handle, sigma_col0 as u32, zs_partial_products.handle, n_routed as u32,
+                                             degree as u32, k_is.as_ptr(), betas.as_ptr(), gammas.as_ptr(), alphas.as_ptr())
+        })
+    }
+
     /// divide by Z_H on the coset, coset_ifft, chunks(degree), `PolynomialBatch::from_coeffs`: the quotient commitment
     pub fn commit(&self, cap_height: usize) -> Result<DeviceTree<'c>, Error> {
         if cap_height > 31 {

@@ -276,3 +276,95 @@ def test_quotient_commit_tail(ctx, oc, log_n):
                 tot = (tot * pow(x, n, P) + ev) % P
             assert tot * zh % P == int(acc[k, rev[i]])
     batch.merkle_tree.free(); wires.merkle_tree.free()
+
+
+def _eval_poly(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + int(c)) % P
+    return acc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n,n_routed,degree", [(4, 80, 8), (5, 12, 4)])
+def test_permutation_argument_end_to_end(ctx, log_n, n_routed, degree):
+    """wires with a copy permutation -> gl_partial_products (Z, partial products) -> three commits -> gl_quotient_add_permutation over the
+    LDE rows (+ a gate, to exercise the offset) -> gl_quotient_commit.  Checked (a) row by row against the restated vanishing terms and
+    (b) the way the VERIFIER checks a proof: at a random point zeta outside the domain, Z_H(zeta) * sum_c zeta^(cN) t_c(zeta) must equal
+    the alpha-combination of the terms computed from the opened polynomial values — which only holds if Z really closes the argument."""
+    import plonky25_b200 as g
+    rnd = random.Random(77 + log_n)
+    n, r, n_ch, n_wires = 1 << log_n, 3, 2, 135
+    w_n = pow(1753635133440165772, 1 << (32 - log_n), P)
+    xs = [pow(w_n, i, P) for i in range(n)]
+    k_is = [pow(7, j, P) for j in range(n_routed)]
+    cells = [(j, i) for j in range(n_routed) for i in range(n)]
+    perm = list(range(len(cells)))
+    rnd.shuffle(perm)
+    sigma_of, wires = {}, [[rnd.randrange(P) for _ in range(n)] for _ in range(n_wires)]
+    for c0 in range(0, len(perm), 3):
+        cyc = [cells[t] for t in perm[c0:c0 + 3]]
+        v = rnd.randrange(P)
+        for a_, b_ in zip(cyc, cyc[1:] + cyc[:1]):
+            sigma_of[a_] = b_
+            wires[a_[0]][a_[1]] = v
+    sigmas = [[k_is[sigma_of[(j, i)][0]] * xs[sigma_of[(j, i)][1]] % P for i in range(n)] for j in range(n_routed)]
+    betas, gammas = [rnd.randrange(P) for _ in range(n_ch)], [rnd.randrange(P) for _ in range(n_ch)]
+    alphas = [rnd.randrange(P) for _ in range(n_ch)]
+    W = np.array(wires, dtype=np.uint64)
+    S = np.array(sigmas, dtype=np.uint64)
+    zs = g.partial_products_and_zs(list(W[:n_routed]), list(S), k_is, betas, gammas, degree, ctx=ctx)
+    n_chunks = -(-n_routed // degree)
+    consts = np.array([[rnd.randrange(P) for _ in range(n)] for _ in range(3)], dtype=np.uint64)
+    wires_b = g.PolynomialBatch.from_values(list(W), r, False, 2, ctx=ctx)
+    sig_b = g.PolynomialBatch.from_values(list(consts) + list(S), r, False, 2, ctx=ctx)       # sigma polynomials at columns [3, 3 + n_routed)
+    zs_b = g.PolynomialBatch.from_values(list(zs), r, False, 2, ctx=ctx)
+    quot = g.Quotient(wires_b, n_ch, ctx=ctx)
+    al = np.array(alphas, dtype=np.uint64)
+    quot.add_permutation(sig_b, 3, zs_b, n_routed, degree, k_is, betas, gammas, alphas)
+    n_terms = n_ch * (1 + n_chunks)
+    acc = quot.values()
+    # (a) sampled LDE rows against the restated terms
+    bits, R = log_n + r, n << r
+    w_R = pow(1753635133440165772, 1 << (32 - bits), P)
+    rev = lambda i: int(format(i, "0%db" % bits)[::-1], 2)
+    for row in [0, 1, R - 1] + [rnd.randrange(R) for _ in range(5)]:
+        idx = rev(row)
+        row_next = rev((idx + (1 << r)) % R)
+        x = 7 * pow(w_R, idx, P) % P
+        lw, ls = wires_b.merkle_tree.get(row).tolist(), sig_b.merkle_tree.get(row).tolist()
+        lz, lzn = zs_b.merkle_tree.get(row).tolist(), zs_b.merkle_tree.get(row_next).tolist()
+        terms = go.vanishing_permutation_terms(lw[:n_routed], ls[3:3 + n_routed], lz, lzn, x, k_is, betas, gammas, degree, log_n)
+        assert len(terms) == n_terms
+        for c in range(n_ch):
+            assert int(acc[c, row]) == go.reduce_with_powers(terms, alphas[c]), (row, c)
+    # a gate on top, at the offset the terms above leave
+    quot.add_gate(g.GATE_U32_ARITHMETIC, 3, al, constraint_offset=n_terms)
+    tq = quot.commit(2)
+    quot.free()
+    # (b) the verifier's identity at a random zeta
+    zeta = rnd.randrange(2, P)
+    gz = zeta * w_n % P
+    cw, cs, cz = wires_b.polynomials, sig_b.polynomials, zs_b.polynomials
+    ew = [_eval_poly(cw[j], zeta) for j in range(n_wires)]
+    es = [_eval_poly(cs[3 + j], zeta) for j in range(n_routed)]
+    ez = [_eval_poly(cz[j], zeta) for j in range(n_ch * n_chunks)]
+    ezn = [_eval_poly(cz[j], gz) for j in range(n_ch * n_chunks)]
+    terms = go.vanishing_permutation_terms(ew[:n_routed], es, ez, ezn, zeta, k_is, betas, gammas, degree, log_n)
+    z_h = (pow(zeta, n, P) - 1) % P
+    # (the u32 gate's constraints do not vanish on H for these random wires, so the identity is checked on a second accumulator that
+    # holds the permutation terms alone; `tq` above only exercises the gate offset and the commit)
+    assert tq.polynomials.shape == (n_ch * 8, n)
+    quot2 = g.Quotient(wires_b, n_ch, ctx=ctx)
+    quot2.add_permutation(sig_b, 3, zs_b, n_routed, degree, k_is, betas, gammas, alphas)
+    t2 = quot2.commit(2)
+    quot2.free()
+    ch2 = t2.polynomials
+    perm_terms = terms[:n_terms]
+    for c in range(n_ch):
+        t_zeta = 0
+        for ch in reversed(range(8)):
+            t_zeta = (t_zeta * pow(zeta, n, P) + _eval_poly(ch2[c * 8 + ch], zeta)) % P
+        assert z_h * t_zeta % P == go.reduce_with_powers(perm_terms, alphas[c]), "Z_H(zeta) t(zeta) != vanishing(zeta): the argument does not close"
+    for b_ in (wires_b, sig_b, zs_b, tq, t2):
+        b_.merkle_tree.free()
