@@ -224,6 +224,11 @@ int gl_fri_pow(gl_ctx* ctx, const uint64_t sponge_state[12], const uint64_t* inp
  * states: n x 12 words, permuted in place, canonical on return.  Used by the host-side Challenger mirror.       */
 int gl_poseidon_permute(gl_ctx* ctx, uint64_t* states, uint64_t n);
 
+/* The Challenger's duplexing loop over n_groups FULL groups of 8 observed elements (iop/challenger.rs · observe_elements): for each group,
+ * state[0..8) <- group; state <- permute(state).  One launch and one round trip per call (a Merkle cap of 16 hashes = 8 groups), state
+ * canonical on return.  The host-side Challenger keeps its input/output buffers and calls this for the full groups.                   */
+int gl_poseidon_absorb(gl_ctx* ctx, uint64_t state[12], const uint64_t* groups, uint32_t n_groups);
+
 /* ---- device-pointer stage API (inputs/outputs already in HBM; multi-GPU host code and benchmarks) ------------- */
 /* whole commit from a device-resident column-major matrix d_cols[n_cols][2^log_n] (col_stride words apart) */
 int gl_dev_commit(gl_ctx* ctx, const uint64_t* d_cols, uint64_t col_stride, uint32_t n_cols, uint32_t log_n,

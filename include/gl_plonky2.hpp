@@ -260,7 +260,21 @@ public:
         input_buffer.push_back(e >= ORDER ? e - ORDER : e);
         if (input_buffer.size() == SPONGE_RATE) duplexing();
     }
-    void observe_elements(const F* es, size_t n) { for (size_t i = 0; i < n; i++) observe_element(es[i]); }
+    /* observe_element for every element; the duplexing of all full groups of 8 runs in ONE device call (gl_poseidon_absorb): the chain of
+     * permutations is sequential anyway, so a Merkle cap costs one launch and one round trip instead of eight */
+    void observe_elements(const F* es, size_t n) {
+        if (n == 0) return;
+        output_buffer.clear();
+        std::vector<F> buf(input_buffer);
+        for (size_t i = 0; i < n; i++) buf.push_back(es[i] >= ORDER ? es[i] - ORDER : es[i]);
+        const size_t n_full = buf.size() / SPONGE_RATE;
+        if (n_full) {
+            ctx_->check(gl_poseidon_absorb(ctx_->raw(), sponge_state.data(), buf.data(), uint32_t(n_full)));
+            output_buffer.assign(sponge_state.begin(), sponge_state.begin() + SPONGE_RATE);
+        }
+        input_buffer.assign(buf.begin() + n_full * SPONGE_RATE, buf.end());
+        if (!input_buffer.empty()) output_buffer.clear();
+    }
     void observe_elements(const std::vector<F>& es) { observe_elements(es.data(), es.size()); }
     void observe_hash(const HashOut& h) { observe_elements(h.elements.data(), 4); }
     void observe_cap(const MerkleCap& cap) { for (const auto& h : cap.hashes) observe_hash(h); }

@@ -70,6 +70,7 @@ SIGNATURES = {
     "gl_partial_products": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32,
                                     c_uint32, c_void_p]),
     "gl_fri_pow": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, POINTER(c_uint64)]),
+    "gl_poseidon_absorb": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32]),
     "gl_poseidon_permute": (c_int, [c_void_p, c_void_p, c_uint64]),
     "gl_dev_commit": (c_int, [c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_uint32, c_int, c_void_p,
                               POINTER(c_uint64)]),

@@ -313,8 +313,23 @@ class Challenger:
             self._duplexing()
 
     def observe_elements(self, es):
-        for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist():
-            self.observe_element(e)
+        """observe_element for every element — with the duplexing of all FULL groups of 8 done in one device call (gl_poseidon_absorb):
+        the chain of permutations is sequential anyway, so a Merkle cap costs one launch and one round trip instead of eight"""
+        vals = [int(e) % P for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist()]
+        if not vals:
+            return
+        self.output_buffer = []
+        buf = self.input_buffer + vals
+        n_full = len(buf) // SPONGE_RATE
+        if n_full:
+            groups = np.array(buf[:n_full * SPONGE_RATE], dtype=np.uint64)
+            st = np.ascontiguousarray(self.sponge_state, dtype=np.uint64)
+            _check(self.ctx, self.ctx.lib.gl_poseidon_absorb(self.ctx.handle, _ptr(st), _ptr(groups), n_full))
+            self.sponge_state = st
+            self.output_buffer = [int(x) for x in st[:SPONGE_RATE]]
+        self.input_buffer = buf[n_full * SPONGE_RATE:]
+        if self.input_buffer:
+            self.output_buffer = []       # an element observed after the last duplexing invalidates the buffered outputs
 
     def observe_hash(self, h):
         self.observe_elements(h)

@@ -2196,6 +2196,21 @@ int gl_poseidon_permute(gl_ctx* c, uint64_t* states, uint64_t n) {
     GL_API_END(c)
 }
 
+int gl_poseidon_absorb(gl_ctx* c, uint64_t state[12], const uint64_t* groups, uint32_t n_groups) {
+    GL_API_BEGIN(c)
+    if (!state || (!groups && n_groups)) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    if (n_groups == 0) return GL_OK;
+    c->scratch.ensure(12 + 8ULL * n_groups);
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p, state, 96, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->scratch.p + 12, groups, 64ULL * n_groups, cudaMemcpyHostToDevice, c->stream));
+    merkle::sponge_absorb_kernel<<<1, 32, 0, c->stream>>>(c->scratch.p, c->scratch.p + 12, n_groups);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(state, c->scratch.p, 96, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return GL_OK;
+    GL_API_END(c)
+}
+
 // element-wise field primitives exactly as the kernels use them (unit tests of the carry logic on adversarial words)
 __global__ void field_op_kernel(int op, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t* __restrict__ out,
                                 uint64_t n) {

@@ -160,6 +160,24 @@ __global__ void permute_kernel(uint64_t* __restrict__ states, uint64_t n) {
     for (int k = 0; k < poseidon::WIDTH; k++) states[12 * i + k] = gl::canon(s[k]);
 }
 
+// The Challenger's duplexing loop for a run of FULL input groups (plonky2 iop/challenger.rs · observe_elements -> duplexing, overwrite
+// mode): state[0..8) <- group k, permute, for k = 0..n_groups.  The chain is strictly sequential (each permutation needs the previous
+// state), so one thread runs it: a single launch and one round trip for a whole Merkle cap (8 groups) instead of one per permutation.
+__global__ void sponge_absorb_kernel(uint64_t* __restrict__ state12, const uint64_t* __restrict__ groups, uint32_t n_groups) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint64_t s[poseidon::WIDTH];
+#pragma unroll
+    for (int k = 0; k < poseidon::WIDTH; k++) s[k] = state12[k];
+#pragma unroll 1
+    for (uint32_t g = 0; g < n_groups; g++) {
+#pragma unroll
+        for (int k = 0; k < poseidon::RATE; k++) s[k] = groups[8 * g + k];
+        poseidon::permute(s);
+    }
+#pragma unroll
+    for (int k = 0; k < poseidon::WIDTH; k++) state12[k] = gl::canon(s[k]);
+}
+
 // K8: FRI proof-of-work grinding (plonky2 fri/prover.rs · fri_proof_of_work).  Candidate w goes to lane
 // `pos` of the pre-absorbed sponge state, one permutation, accept when canonical state[7] has >= min_lz leading zero
 // bits.  One thread per candidate of the window [base, base + n); the smallest accepted candidate wins (atomicMin), which

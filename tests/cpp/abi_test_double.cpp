@@ -91,6 +91,15 @@ int gl_poseidon_permute(gl_ctx*, uint64_t* states, uint64_t n) {
     return GL_OK;
 }
 
+int gl_poseidon_absorb(gl_ctx*, uint64_t state[12], const uint64_t* groups, uint32_t n_groups) {
+    for (uint32_t g = 0; g < n_groups; g++) {
+        for (int k = 0; k < 8; k++) state[k] = groups[8 * g + k] % P;
+        for (int k = 8; k < 12; k++) state[k] %= P;
+        glo_poseidon(state);
+    }
+    return GL_OK;
+}
+
 int gl_commit(gl_ctx* c, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height, int input_is_coeffs,
               uint64_t* out_coeffs, uint64_t* out_leaves, uint64_t* out_digests, uint64_t* out_cap, gl_handle* out_batch) {
     if (!n_cols) return c->fail(GL_ERR_INVALID, "empty polynomial batch");
