@@ -33,8 +33,8 @@ def test_poseidon_random_and_non_canonical(ctx, oc):
     states[1, :] = np.uint64(P)
     states[2, :] = np.uint64(P - 1)
     out = ctx.poseidon_permute(states)
-    for i in list(range(8)) + [100, 4095]:
-        assert out[i].tolist() == oc.poseidon(states[i]).tolist()
+    for i in range(states.shape[0]):                 # every one of the 4096 states against the C oracle
+        assert out[i].tolist() == oc.poseidon(states[i] % np.uint64(P)).tolist(), i
     assert (out < np.uint64(P)).all()
 
 
