@@ -330,6 +330,59 @@ def run_wrapper(a):
                      "unit": "wire elements of the LDE rows consumed per second (R x 135 / kernel time, CUDA events)",
                      "parity": {"sampled_rows": len(rows), "match": bool(ok),
                                 "oracle": "oracle/gates_oracle.py (restates poseidon2_gate.rs:233-310, arithmetic_u32.rs:103-166)"}}
+        # ---- SURVEY §8(f) rank 4 + the permutation part of rank 3, at the same shape: Z / partial products of 80 routed wires (2 challenges,
+        # chunks of 8), their commit, and the permutation-argument terms over the R = 2^19 resident LDE rows.  Sigma VALUES are synthetic
+        # (the 86-column batch's first 80 columns), so the argument does not close; parity is per row against the restated formulas.
+        n_routed, degree, n = 80, 8, 1 << log_n
+        k_is = [pow(7, j, P) for j in range(n_routed)]
+        betas, gammas = [0x1111111122222222 % P, 0x3333333344444444 % P], [0x5555555566666666 % P, 0x7777777788888888 % P]
+        sig_cols = [pinned[0][j] for j in range(n_routed)]
+        t_pp = []
+        for _ in range(3):
+            ta = time.perf_counter()
+            zs = g.partial_products_and_zs([pinned[1][j] for j in range(n_routed)], sig_cols, k_is, betas, gammas, degree, ctx=ctx)
+            t_pp.append((time.perf_counter() - ta) * 1e3)
+        lib.gl_ctx_aux_ms(ctx.handle, ctypes.byref(ms_))
+        pp_kernel_ms = ms_.value
+        # rows i: the chunk quotients recomputed from the definition must be the ratios of consecutive outputs
+        w_n = pow(1753635133440165772, 1 << (32 - log_n), P)
+        ok_pp = True
+        for i in [0, 1, n - 2] + [rnd.randrange(n - 1) for _ in range(5)]:
+            x = pow(w_n, i, P)
+            for k in range(2):
+                accs = [int(zs[k, i])] + [int(zs[2 + k * 9 + c, i]) for c in range(9)] + [int(zs[k, i + 1])]
+                for c in range(10):
+                    num = den = 1
+                    for j in range(8 * c, 8 * c + 8):
+                        wv = int(pinned[1][j][i])
+                        num = num * ((wv + betas[k] * k_is[j] % P * x + gammas[k]) % P) % P
+                        den = den * ((wv + betas[k] * int(sig_cols[j][i]) + gammas[k]) % P) % P
+                    ok_pp = ok_pp and accs[c] * num % P == accs[c + 1] * den % P
+        wires = g.PolynomialBatch.from_values(list(pinned[1]), 3, False, 4, ctx=ctx)
+        sig_b = g.PolynomialBatch.from_values(list(pinned[0]), 3, False, 4, ctx=ctx)
+        zs_b = g.PolynomialBatch.from_values(list(zs), 3, False, 4, ctx=ctx)
+        quot = g.Quotient(wires, 2, ctx=ctx)
+        t_v = min(quot.add_permutation(sig_b, 0, zs_b, n_routed, degree, k_is, betas, gammas, [int(a_) for a_ in alphas]) for _ in range(3))
+        accq = quot.values()
+        quot.free()
+        bits = log_n + 3
+        w_R = pow(1753635133440165772, 1 << (32 - bits), P)
+        rev = lambda i: int(format(i, "0%db" % bits)[::-1], 2)
+        ok_v = True
+        for row in [0, R - 1] + [rnd.randrange(R) for _ in range(6)]:
+            idx = rev(row)
+            x = 7 * pow(w_R, idx, P) % P
+            lw, ls = wires.merkle_tree.get(row).tolist(), sig_b.merkle_tree.get(row).tolist()
+            lz, lzn = zs_b.merkle_tree.get(row).tolist(), zs_b.merkle_tree.get(rev((idx + 8) % R)).tolist()
+            terms = go.vanishing_permutation_terms(lw[:n_routed], ls[:n_routed], lz, lzn, x, k_is, betas, gammas, degree, log_n)
+            for k in range(2):
+                ok_v = ok_v and int(accq[k, row]) == 3 * go.reduce_with_powers(terms, int(alphas[k])) % P
+        for b_ in (wires, sig_b, zs_b):
+            b_.merkle_tree.free()
+        gate_eval["permutation"] = {"partial_products_call_ms": round(min(t_pp), 3), "partial_products_kernels_ms": round(pp_kernel_ms, 3),
+                                    "vanishing_terms_kernel_ms": round(t_v, 4), "n_routed": n_routed, "degree": degree,
+                                    "note": "partial_products_call_ms includes 84 MB of host->device columns and 10 MB back",
+                                    "parity": {"partial_products_rows": bool(ok_pp), "vanishing_terms_rows": bool(ok_v)}}
     except Exception as e:   # a reported extra: never lose the main line over it
         gate_eval = {"error": repr(e)}
     line.update({"value": round(ms, 3), "ms_per_step": round(ms, 3), "stage_ms": {k: round(v / a.steps, 3) for k, v in acc.items()},
