@@ -14,6 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "plonky2.5_b200", "variants")
 VARIANTS = {
     "default":        [],
+    "lb64":           ["-DLEAF_BLOCK=64", "-DLEAF_MIN_BLOCKS=12"],
+    "lb256":          ["-DLEAF_BLOCK=256", "-DLEAF_MIN_BLOCKS=3"],
+    "mb5":            ["-DLEAF_MIN_BLOCKS=5"],
+    "mb7":            ["-DLEAF_MIN_BLOCKS=7"],
+    "mb8":            ["-DLEAF_MIN_BLOCKS=8"],
 }
 
 
