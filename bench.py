@@ -567,12 +567,15 @@ def main():
                 lib.gl_tree_free(ctx.handle, hd.value)
             h2d = cols * n * 8
         else:
-            harr = torch.empty((c1 - c0, n), dtype=torch.int64).pin_memory()
-            harr.copy_(d_cols)
+            idx = state.host_columns()       # the streamed coset plan deals the host columns cyclically (ShardPlan.stream_columns)
+            harr = torch.empty((len(idx), n), dtype=torch.int64).pin_memory()
+            full = synth_columns(torch, dev, cols, n, 1)
+            harr.copy_(full[torch.tensor(idx, device=dev)] if idx else full[:0])
+            del full
 
             def e2e_step():
-                cap[:] = state.commit_host(harr)     # fused mode: chunked H2D behind the NTTs (gl_lde_scatter)
-            h2d = (c1 - c0) * n * 8
+                cap[:] = state.commit_host(harr)     # chunked / streamed H2D behind the NTTs and the hashing
+            h2d = len(idx) * n * 8
         for _ in range(2):
             e2e_step()
         barrier()
@@ -594,7 +597,8 @@ def main():
                "stage_ms_last_call_rank0": {k: round(v, 3) for k, v in e2e_stage_ms.items() if v},
                "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
-                      if world == 1 else "ShardedCommit.commit_host: pinned host shard -> gl_lde_scatter (chunked H2D overlapped with the NTTs) -> hash -> cap to host; plan: "
+                      if world == 1 else "ShardedCommit.commit_host: pinned host columns -> gl_commit_coset_stream (waves: H2D, iNTT, NVLink pulls and own-coset NTTs of "
+                      "wave w+1 behind the hashing of wave w) or gl_lde_scatter (chunked H2D behind the NTTs) -> cap to host; plan: "
                       + (state._host_impl.exchange if state._host_impl is not None else state.exchange)}
 
     if world > 1:

@@ -275,6 +275,38 @@ int gl_dev_lde_own_cosets(gl_ctx* ctx, uint64_t* const* peer_coeffs, uint64_t* c
                           const uint32_t* col_counts, const uint32_t* col_offsets, uint32_t n_peers, uint32_t self, uint32_t log_n,
                           uint32_t rate_bits, uint64_t* d_leaves, uint32_t leaf_pitch);
 
+/* ---- the coset-sharded commit, STREAMED from host columns (one process per GPU; what a multi-GPU PolynomialBatch::from_values pays) ----
+ * With host inputs the plan above cannot start before every rank's whole shard has crossed PCIe.  Here the batch is cut into WAVES of
+ * n_peers * group_width consecutive columns; in wave w rank q owns the group_width columns [gw*(w*G+q), gw*(w*G+q+1)) (cyclic deal).
+ * Per wave every rank copies its group host->device, runs its iNTT on a high-priority stream and publishes a ticket to every peer
+ * (csrc/peer_sync.cuh: release stores into the peers' flag arrays, no host round trip, no collective); the peers' copy engines pull the
+ * group over NVLink as soon as the ticket shows; the rank then evaluates ITS OWN cosets of the wave's G groups and ABSORBS the wave's
+ * columns into the leaf sponge (the overwrite-mode sponge consumes a leaf strictly left to right).  Copies, pulls and NTTs of wave w+1
+ * run while wave w is hashed, so only the first wave's copy is exposed; the tree above the digests follows the last wave.
+ * Same permutations in the same order as the one-GPU commit => the same digests and cap, bit for bit.
+ *
+ * Buffers: every rank exports ONE buffer (gl_dev_ipc_alloc, zero-filled) of `exported_words` = n_waves * N * gw coefficient words
+ * followed by n_peers * n_waves ticket words; peer_bufs[q] = rank q's (own pointer for q == self).  d_stage = `stage_words` local words
+ * (the pulled groups), d_leaves = [rows_per_rank][leaf_pitch], d_digests as gl_dev_merkle.  own_cols = the rank's columns in wave order
+ * (gl_stream_plan_sizes reports how many).  epoch: the number of earlier calls on these buffers — the same on every rank.  The caller must
+ * put a collective (the cap all-gather) between two calls, as for gl_dev_lde_own_cosets.  A peer that does not publish within
+ * GL_PEER_TIMEOUT_MS (default 20000) makes the call fail with GL_ERR_CUDA instead of hanging. */
+typedef struct {
+    uint32_t n_cols;       /* C: columns of the WHOLE batch */
+    uint32_t log_n;
+    uint32_t rate_bits;
+    uint32_t cap_height;   /* of the rank's own leaf range (global cap height - log2 n_peers) */
+    uint32_t n_peers;      /* G, a power of two <= 2^rate_bits */
+    uint32_t self;
+    uint32_t group_width;  /* gw: 4 or 8 */
+    uint32_t leaf_pitch;   /* words per device leaf row, multiple of 8, >= round_up(C, 8) */
+    uint64_t epoch;
+} gl_stream_plan_t;
+int gl_stream_plan_sizes(const gl_stream_plan_t* plan, uint64_t* exported_words, uint64_t* stage_words, uint32_t* n_waves,
+                         uint32_t* n_own_cols);
+int gl_commit_coset_stream(gl_ctx* ctx, const gl_stream_plan_t* plan, const uint64_t* const* own_cols, int input_is_coeffs,
+                           uint64_t* const* peer_bufs, uint64_t* d_stage, uint64_t* d_leaves, uint64_t* d_digests, uint64_t* out_cap);
+
 /* CUDA IPC plumbing for the above: export a device buffer (64-byte handle) / map a peer's / unmap / free */
 int gl_dev_ipc_alloc(gl_ctx* ctx, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]);
 int gl_dev_ipc_open(gl_ctx* ctx, const uint8_t handle[64], uint64_t** out_ptr);

@@ -22,6 +22,12 @@ class TreeInfo(ctypes.Structure):
                 ("rate_bits", c_uint32), ("has_coeffs", c_uint32), ("pitch", c_uint32)]
 
 
+class StreamPlan(ctypes.Structure):
+    """gl_stream_plan_t (include/gl_commit.h): the streamed coset-sharded commit of one rank"""
+    _fields_ = [("n_cols", c_uint32), ("log_n", c_uint32), ("rate_bits", c_uint32), ("cap_height", c_uint32), ("n_peers", c_uint32),
+                ("self", c_uint32), ("group_width", c_uint32), ("leaf_pitch", c_uint32), ("epoch", c_uint64)]
+
+
 u64p = POINTER(c_uint64)
 
 # name -> (restype, argtypes); every symbol include/gl_commit.h declares
@@ -83,6 +89,9 @@ SIGNATURES = {
     "gl_intt_host": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_uint32, c_int, c_void_p, c_uint32]),
     "gl_dev_lde_own_cosets": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32),
                                       c_uint32, c_uint32, c_uint32, c_uint32, c_void_p, c_uint32]),
+    "gl_stream_plan_sizes": (c_int, [POINTER(StreamPlan), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint32), POINTER(c_uint32)]),
+    "gl_commit_coset_stream": (c_int, [c_void_p, POINTER(StreamPlan), POINTER(c_void_p), c_int, POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
     "gl_dev_ipc_alloc": (c_int, [c_void_p, c_uint64, POINTER(c_void_p), c_void_p]),
     "gl_dev_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "gl_dev_ipc_close": (c_int, [c_void_p, c_void_p]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgl_commit.so")
 SOURCES = ["gl_commit.cu"]
-HEADERS = ["gl_field.cuh", "poseidon.cuh", "poseidon_constants.cuh", "merkle.cuh", "ntt.cuh", "ntt2.cuh", "gates.cuh", "permutation.cuh", "poseidon2_constants.cuh", "fri.cuh", "microbench.cuh", "openings.cuh"]
+HEADERS = ["gl_field.cuh", "poseidon.cuh", "poseidon_constants.cuh", "merkle.cuh", "ntt.cuh", "ntt2.cuh", "gates.cuh", "permutation.cuh", "poseidon2_constants.cuh", "fri.cuh", "microbench.cuh", "openings.cuh", "peer_sync.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -29,6 +29,7 @@
 #include "ntt.cuh"
 #include "ntt2.cuh"
 #include "openings.cuh"
+#include "peer_sync.cuh"
 #include "permutation.cuh"
 
 namespace {
@@ -229,7 +230,8 @@ struct gl_ctx {
     bool trace = false;                    // GL_TRACE=1: per-coset timeline of the overlapped exchange on stderr (development aid)
     std::vector<cudaEvent_t> trace_ev;     // base, then per coset: ntt start, ntt end, send start, send end
     cudaEvent_t ev_sync = nullptr, ev_copyback = nullptr;
-    std::vector<cudaEvent_t> chunk_ev, pull_ev;
+    std::vector<cudaEvent_t> chunk_ev, pull_ev, own_ev;
+    DevBuf sync_err;                      // error word of the streamed coset plan's ticket waits (peer_sync.cuh)
     cudaEvent_t ev[GL_N_STAGES + 1] = {};
     float stage_ms[GL_N_STAGES] = {};
     uint32_t launches[GL_N_STAGES] = {};
@@ -857,11 +859,12 @@ void gl_ctx_destroy(gl_ctx* c) {
     c->pass_roots.clear();
     c->lde_tables.clear();
     c->coset_cache.clear();
-    c->in_stage.release(); c->vals.release(); c->scratch.release(); c->hash_state.release();
+    c->in_stage.release(); c->vals.release(); c->scratch.release(); c->hash_state.release(); c->sync_err.release();
     DevPool::get().trim(c->device);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->pull_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->own_ev) if (e) cudaEventDestroy(e);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->ev_copyback) cudaEventDestroy(c->ev_copyback);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1136,6 +1139,171 @@ int gl_dev_lde_own_cosets(gl_ctx* c, uint64_t* const* peer_coeffs, uint64_t* con
     GL_API_END(c)
 }
 
+// ---- coset-sharded commit streamed from host columns (include/gl_commit.h · gl_commit_coset_stream) ---------------------------------
+namespace {
+struct StreamLayout {
+    uint32_t G, gw, n_groups, W, C;
+    bool has(uint32_t q, uint32_t w) const { return w * G + q < n_groups; }
+    uint32_t cols(uint32_t q, uint32_t w) const { return has(q, w) ? std::min(gw, C - gw * (w * G + q)) : 0; }
+    uint32_t own_cols(uint32_t q) const { uint32_t n = 0; for (uint32_t w = 0; w < W; w++) n += cols(q, w); return n; }
+};
+StreamLayout stream_layout(const gl_stream_plan_t* p) {
+    if (!p) GL_THROW(GL_ERR_INVALID, "plan is NULL");
+    if (p->group_width != 4 && p->group_width != 8) GL_THROW(GL_ERR_INVALID, "group_width must be 4 or 8");
+    if (p->n_peers == 0 || (p->n_peers & (p->n_peers - 1)) || p->n_peers > (uint32_t)ntt::MAX_PEERS || p->self >= p->n_peers)
+        GL_THROW(GL_ERR_INVALID, "bad peer count / rank");
+    if (p->n_peers > (1u << p->rate_bits)) GL_THROW(GL_ERR_INVALID, "coset sharding needs n_peers <= 2^rate_bits");
+    if (p->n_cols <= 4) GL_THROW(GL_ERR_UNSUPPORTED, "leaves of <= 4 elements are not hashed (hash_or_noop): use gl_dev_merkle");
+    if (p->log_n + p->rate_bits > 31) GL_THROW(GL_ERR_UNSUPPORTED, "log_n + rate_bits > 31");
+    if (p->leaf_pitch % 8 || p->leaf_pitch < round_up(p->n_cols, 8u)) GL_THROW(GL_ERR_INVALID, "leaf_pitch must be a multiple of 8 and >= round_up(n_cols, 8)");
+    const uint32_t log_rows = p->log_n + p->rate_bits - log2_exact(p->n_peers);
+    if (p->cap_height > log_rows) GL_THROW(GL_ERR_INVALID, "cap_height should be at most log2(leaves.len()) of the rank's leaf range");
+    StreamLayout L;
+    L.G = p->n_peers; L.gw = p->group_width; L.C = p->n_cols;
+    L.n_groups = (p->n_cols + L.gw - 1) / L.gw;
+    L.W = (L.n_groups + L.G - 1) / L.G;
+    return L;
+}
+}  // namespace
+
+int gl_stream_plan_sizes(const gl_stream_plan_t* plan, uint64_t* exported_words, uint64_t* stage_words, uint32_t* n_waves, uint32_t* n_own_cols) {
+    try {
+        const StreamLayout L = stream_layout(plan);
+        const uint64_t N = 1ULL << plan->log_n;
+        if (exported_words) *exported_words = (uint64_t)L.W * N * L.gw + (uint64_t)L.G * L.W;
+        if (stage_words) *stage_words = (uint64_t)L.G * L.W * N * L.gw;
+        if (n_waves) *n_waves = L.W;
+        if (n_own_cols) *n_own_cols = L.own_cols(plan->self);
+        return GL_OK;
+    } catch (const GlError& e) {
+        return e.code;
+    }
+}
+
+int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64_t* const* own_cols, int input_is_coeffs,
+                           uint64_t* const* peer_bufs, uint64_t* d_stage, uint64_t* d_leaves, uint64_t* d_digests, uint64_t* out_cap) {
+    GL_API_BEGIN(c)
+    const StreamLayout L = stream_layout(plan);
+    if (!peer_bufs || !d_stage || !d_leaves || !d_digests || !out_cap) GL_THROW(GL_ERR_INVALID, "NULL pointer");
+    const uint32_t G = L.G, gw = L.gw, W = L.W, self = plan->self, log_n = plan->log_n, rate_bits = plan->rate_bits, C = L.C;
+    const uint32_t n_own = L.own_cols(self);
+    if (n_own && !own_cols) GL_THROW(GL_ERR_INVALID, "own_cols is NULL");
+    for (uint32_t j = 0; j < n_own; j++)
+        if (!own_cols[j]) GL_THROW(GL_ERR_INVALID, "own_cols[%u] is NULL", j);
+    for (uint32_t q = 0; q < G; q++)
+        if (!peer_bufs[q]) GL_THROW(GL_ERR_INVALID, "peer %u: NULL buffer", q);
+    const uint64_t N = 1ULL << log_n, blk = N * gw;                     // words of one (rank, wave) coefficient block [N][gw]
+    const uint32_t blocks_per_rank = (1u << rate_bits) / G, first_block = self * blocks_per_rank;
+    const uint64_t rows = (uint64_t)blocks_per_rank * N;
+    const uint32_t cap_height = plan->cap_height, leaf_pitch = plan->leaf_pitch;
+    const uint64_t flags_off = (uint64_t)W * blk;
+    uint64_t* own_buf = peer_bufs[self];
+    get_roots(c, log_n);
+    const auto& tabs = get_lde_tables(c, log_n, rate_bits);
+    c->in_stage.ensure(blk * W);
+    if (!input_is_coeffs) c->vals.ensure(blk * W);
+    c->hash_state.ensure(12 * rows);
+    c->scratch.ensure(std::max<uint64_t>(4ULL << cap_height, 1));      // device cap
+    c->sync_err.ensure(1);
+    uint64_t* d_cap = c->scratch.p;
+    auto grow = [](std::vector<cudaEvent_t>& v, size_t n) {
+        size_t old = v.size();
+        if (old >= n) return;
+        v.resize(n, nullptr);
+        for (size_t i = old; i < n; i++) CUDA_CHECK(cudaEventCreateWithFlags(&v[i], cudaEventDisableTiming));
+    };
+    grow(c->chunk_ev, W); grow(c->own_ev, W); grow(c->pull_ev, (size_t)W * G);
+    uint64_t timeout_ns = 20000ULL * 1000000ULL;
+    if (const char* m = getenv("GL_PEER_TIMEOUT_MS")) timeout_ns = strtoull(m, nullptr, 10) * 1000000ULL;
+    const uint64_t ticket0 = plan->epoch * W + 1;                        // wave w publishes ticket0 + w
+    memset(c->launches, 0, sizeof c->launches);
+    memset(c->stage_ms, 0, sizeof c->stage_ms);
+
+    record(c, GL_STAGE_H2D);
+    CUDA_CHECK(cudaMemsetAsync(c->sync_err.p, 0, 8, c->stream));
+    CUDA_CHECK(cudaEventRecord(c->ev_sync, c->stream));                  // staging / in_stage may still be read by an earlier call
+    for (cudaStream_t st : {c->copy_stream, c->send_stream, c->pull_stream}) CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_sync, 0));
+
+    // (1) copy stream: the own group of every wave, host -> device
+    for (uint32_t w = 0, j = 0; w < W; w++) {
+        for (uint32_t k = 0; k < L.cols(self, w); k++, j++)
+            CUDA_CHECK(cudaMemcpyAsync(c->in_stage.p + w * blk + (uint64_t)k * N, own_cols[j], N * 8, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_CHECK(cudaEventRecord(c->chunk_ev[w], c->copy_stream));
+    }
+    // (2) high-priority stream: transpose + iNTT of the own group into the exported block, then the ticket to every peer.  These few CTAs
+    //     take SM slots as hashing CTAs retire, so a group is published as soon as it has landed, whatever the compute stream is doing.
+    {
+        struct UseStream {
+            gl_ctx* c; cudaStream_t saved;
+            UseStream(gl_ctx* c, cudaStream_t s) : c(c), saved(c->stream) { c->stream = s; }
+            ~UseStream() { c->stream = saved; }
+        } on_prep(c, c->send_stream);
+        for (uint32_t w = 0; w < W; w++) {
+            const uint32_t nc = L.cols(self, w);
+            if (!nc) continue;
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[w], 0));
+            uint64_t* block = own_buf + w * blk;
+            dim3 tb(32, 8), tg((uint32_t)((N + 31) / 32), (gw + 31) / 32);
+            ntt::transpose_in_kernel<<<tg, tb, 0, c->stream>>>(c->in_stage.p + w * blk, N, input_is_coeffs ? block : c->vals.p + w * blk, gw, gw, nc, N);
+            CUDA_CHECK(cudaGetLastError());
+            c->launches[GL_STAGE_TRANSPOSE]++;
+            if (!input_is_coeffs) run_ntt(c, c->vals.p + w * blk, gw, block, gw, gw, log_n, true, nullptr, (int)gw, &c->launches[GL_STAGE_INTT]);
+            CUDA_CHECK(cudaEventRecord(c->own_ev[w], c->stream));
+            if (G > 1) {
+                peersync::Slots s{};
+                for (uint32_t q = 0; q < G; q++) s.p[q] = q == self ? nullptr : peer_bufs[q] + flags_off + (uint64_t)self * W + w;
+                peersync::signal_kernel<<<1, 32, 0, c->stream>>>(s, G, ticket0 + w);
+                CUDA_CHECK(cudaGetLastError());
+            }
+        }
+    }
+    // (3) pull stream: wait for the peer's ticket in the OWN flag array, then one contiguous copy-engine pull per (wave, peer), nearest
+    //     neighbour first (at any moment every rank reads from a different peer)
+    for (uint32_t w = 0; w < W; w++)
+        for (uint32_t k = 1; k < G; k++) {
+            const uint32_t q = (self + k) % G;
+            if (!L.has(q, w)) continue;
+            peersync::wait_kernel<<<1, 1, 0, c->pull_stream>>>(own_buf + flags_off + (uint64_t)q * W + w, ticket0 + w, reinterpret_cast<uint32_t*>(c->sync_err.p),
+                                                              timeout_ns);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(d_stage + ((uint64_t)q * W + w) * blk, peer_bufs[q] + w * blk, blk * 8, cudaMemcpyDefault, c->pull_stream));
+            CUDA_CHECK(cudaEventRecord(c->pull_ev[(size_t)w * G + q], c->pull_stream));
+        }
+    // (4) compute stream: own cosets of the wave's groups as they arrive (own group first), then the wave's columns into the leaf sponge
+    bool started = false;
+    for (uint32_t w = 0; w < W; w++) {
+        for (uint32_t k = 0; k < G; k++) {
+            const uint32_t q = (self + k) % G;
+            if (!L.has(q, w)) continue;
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, q == self ? c->own_ev[w] : c->pull_ev[(size_t)w * G + q], 0));
+            if (!started) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); started = true; }   // h2d = until the first group is ready
+            uint64_t* coeffs = q == self ? own_buf + w * blk : d_stage + ((uint64_t)q * W + w) * blk;
+            for (uint32_t b = 0; b < blocks_per_rank; b++) {
+                const uint32_t s = h_bitrev(first_block + b, rate_bits);   // leaf block b of the batch is LDE coset bitrev_r(b)
+                uint64_t* dst = d_leaves + (uint64_t)b * N * leaf_pitch + (uint64_t)gw * (w * G + q);
+                run_ntt(c, coeffs, gw, dst, leaf_pitch, gw, log_n, false, &tabs[s], (int)gw, &c->launches[GL_STAGE_LDE]);
+            }
+        }
+        const uint32_t c0 = w * G * gw, c1 = std::min(C, (w + 1) * G * gw);
+        leaf_absorb(c, d_leaves, rows, C, leaf_pitch, cap_height, c0, c1, c->hash_state.p, d_digests, d_cap, w == 0, w + 1 == W, &c->launches[GL_STAGE_LEAF_HASH]);
+    }
+    record(c, GL_STAGE_LEAF_HASH);
+    record(c, GL_STAGE_TREE);
+    merkle_levels(c, rows, cap_height, d_digests, d_cap, &c->launches[GL_STAGE_TREE]);
+    record(c, GL_STAGE_D2H);
+    uint64_t err = 0;
+    CUDA_CHECK(cudaMemcpyAsync(out_cap, d_cap, 32ULL << cap_height, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&err, c->sync_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    record(c, GL_N_STAGES);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->send_stream));                   // (both idle by dependency; the host buffers are only borrowed)
+    CUDA_CHECK(cudaStreamSynchronize(c->pull_stream));
+    for (int i = 0; i < GL_N_STAGES; i++) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    if (err) GL_THROW(GL_ERR_CUDA, "a peer did not publish its coefficient group within the time limit (GL_PEER_TIMEOUT_MS)");
+    return GL_OK;
+    GL_API_END(c)
+}
+
 // ---- CUDA IPC: one process per GPU, each exports its leaf buffer and maps its peers' (NVLink peer access) -----------
 int gl_dev_ipc_alloc(gl_ctx* c, uint64_t words, uint64_t** out_ptr, uint8_t out_handle[64]) {
     GL_API_BEGIN(c)
@@ -1146,6 +1314,8 @@ int gl_dev_ipc_alloc(gl_ctx* c, uint64_t words, uint64_t** out_ptr, uint8_t out_
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) { cudaFree(p); CUDA_CHECK(e); }
+    CUDA_CHECK(cudaMemsetAsync(p, 0, words * 8, c->stream));   // the streamed coset plan keeps its ticket words here: they must start at 0
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     memcpy(out_handle, &h, 64);
     *out_ptr = p;
     c->own_ipc.insert(p);

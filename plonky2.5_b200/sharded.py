@@ -69,6 +69,25 @@ class ShardPlan:
     def recv_splits(self, rank: int) -> List[int]:
         return [self.rows_per_rank * self.pitches[q] for q in range(self.world)]
 
+    # ---- streamed coset plan (include/gl_commit.h · gl_commit_coset_stream): columns dealt cyclically in groups of gw, waves of G groups ----
+    def stream_group_width(self) -> int:
+        """8-column groups when that still leaves >= 4 waves to pipeline (the NTT's preferred tile), else 4"""
+        return 8 if self.n_cols >= 4 * 8 * self.world else 4
+
+    def stream_waves(self) -> int:
+        gw = self.stream_group_width()
+        n_groups = (self.n_cols + gw - 1) // gw
+        return (n_groups + self.world - 1) // self.world
+
+    def stream_columns(self, rank: int) -> List[int]:
+        """global indices of the columns rank `rank` supplies to the streamed plan, in the order it supplies them (wave by wave)"""
+        gw = self.stream_group_width()
+        out = []
+        for w in range(self.stream_waves()):
+            g0 = gw * (w * self.world + rank)
+            out.extend(range(g0, min(g0 + gw, self.n_cols)))
+        return out
+
     def digests_per_rank(self) -> int:
         return 2 * (self.rows_per_rank - (1 << self.local_cap_height))
 
@@ -136,6 +155,11 @@ class ShardedCommit:
         self._first_coset = int(format(j, "0%db" % p.rate_bits)[::-1], 2) if p.rate_bits else 0
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._coeff_ptr = None
+        self._epoch = 0
+        if exchange == "stream":
+            if p.world <= (1 << p.rate_bits) and p.n_cols > 4 and self._init_stream(dev):
+                return
+            self.exchange = exchange = "p2p"
         if exchange == "coset" and p.world <= (1 << p.rate_bits) and self._init_coset(dev):
             return
         if exchange == "coset":
@@ -161,6 +185,25 @@ class ShardedCommit:
         self._stage_ptrs = (ctypes.c_void_p * p.world)(*[0 if t is None else t.data_ptr() for t in self._stage])
         u32 = ctypes.c_uint32 * p.world
         self._pitches, self._counts, self._offsets = u32(*p.pitches), u32(*p.col_counts), u32(*p.col_offsets)
+        self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=torch.int64, device=dev)
+        self.leaves_ptr = self.leaves.data_ptr()
+        return True
+
+    def _init_stream(self, dev) -> bool:
+        """Streamed coset plan (include/gl_commit.h · gl_commit_coset_stream): one exported buffer per rank (coefficient groups + ticket words),
+        local staging for the pulled groups, the own leaf range.  Collective; False on every rank if any rank failed."""
+        from ._lib import StreamPlan
+        p, torch, lib = self.plan, self.torch, self.ctx.lib
+        self._splan = StreamPlan(p.n_cols, p.log_n, p.rate_bits, p.local_cap_height, p.world, self.rank, p.stream_group_width(), p.leaf_pitch, 0)
+        exported, stage, waves, n_own = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(lib.gl_stream_plan_sizes(ctypes.byref(self._splan), ctypes.byref(exported), ctypes.byref(stage), ctypes.byref(waves),
+                                             ctypes.byref(n_own)))
+        assert waves.value == p.stream_waves() and n_own.value == len(p.stream_columns(self.rank))
+        if not self._map_peers(dev, exported.value):
+            return False
+        self._coeff_ptr, self._peer_coeffs = self.leaves_ptr, self._peer_ptrs     # the exported buffer holds coefficient groups + tickets
+        self._peer_ptrs = None
+        self._stage_all = torch.empty(stage.value, dtype=torch.int64, device=dev)
         self.leaves = torch.zeros(p.rows_per_rank * p.leaf_pitch, dtype=torch.int64, device=dev)
         self.leaves_ptr = self.leaves.data_ptr()
         return True
@@ -235,6 +278,8 @@ class ShardedCommit:
         ncg = p.col_counts[self.rank]
         assert d_cols.shape == (ncg, n) and d_cols.is_contiguous()
         t0 = time.perf_counter()
+        if self.exchange == "stream":
+            raise ValueError("the streamed plan takes HOST columns (commit_host); device-resident columns use exchange='coset'")
         if self.exchange == "coset":
             # iNTT of the own column shard into the exported coefficient block; a stream-ordered 1-element all-reduce tells every rank
             # that all blocks are complete; then pull + evaluate the own cosets of every block (pulls overlap the NTTs).  Nobody rewrites
@@ -289,19 +334,25 @@ class ShardedCommit:
         fused mode the shard crosses PCIe in chunks behind the NTTs of the previous chunk (gl_lde_scatter)."""
         p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
         n = 1 << p.log_n
-        ncg = p.col_counts[self.rank]
-        assert tuple(h_cols.shape) == (ncg, n) and h_cols.is_contiguous() and not h_cols.is_cuda
-        if self.exchange == "coset" and self._auto:
-            # HOST columns: in the coset plan nothing can start before every rank's whole shard has crossed PCIe and gone through the
-            # iNTT, whereas the column->row plan hides the copy behind the LDE NTTs chunk by chunk (gl_lde_scatter) — so with
-            # exchange="auto" host inputs take that plan (its buffers are created on first use and kept).  Measured at 8 GPUs: the two are
-            # equal there (21.2 vs 21.5 ms per commit) because eight concurrent host->device copies share the host's PCIe/memory path
-            # (~20 GB/s per GPU instead of ~50), so the shard's copy is as long as the whole LDE stage either way
-            if self._host_impl is None:
-                self._host_impl = ShardedCommit(self.ctx, self.plan, self.rank, self.dist, self.torch, exchange="p2p")
-            out = self._host_impl.commit_host(h_cols)
-            self.digests = self._host_impl.digests
+        if self._auto:
+            # HOST columns: in the coset plan nothing can start before every rank's whole shard has crossed PCIe and gone through the iNTT,
+            # so with exchange="auto" host inputs take the STREAMED coset plan (gl_commit_coset_stream: copies, pulls and NTTs of wave w+1
+            # run while wave w is hashed), or the column->row plan when there are more ranks than cosets / peer mapping fails.  The
+            # buffers are created on first use and kept.
+            impl = self._host()
+            out = impl.commit_host(h_cols)
+            self.digests = impl.digests
             return out
+        ncg = len(self.host_columns())
+        assert tuple(h_cols.shape) == (ncg, n) and h_cols.is_contiguous() and not h_cols.is_cuda
+        if self.exchange == "stream":
+            base = h_cols.data_ptr()
+            ptrs = (ctypes.c_void_p * max(ncg, 1))(*[base + 8 * n * j for j in range(ncg)])
+            self._splan.epoch = self._epoch
+            self._epoch += 1
+            self._check(lib.gl_commit_coset_stream(h, ctypes.byref(self._splan), ptrs, 0, self._peer_coeffs, self._stage_all.data_ptr(),
+                                                   self.leaves_ptr, self.digests.data_ptr(), self.cap_local.ctypes.data))
+            return self._gather_cap()
         if self.exchange == "coset":
             base = h_cols.data_ptr()
             ptrs = (ctypes.c_void_p * ncg)(*[base + 8 * n * j for j in range(ncg)])
@@ -319,12 +370,30 @@ class ShardedCommit:
             self.dist.all_reduce(self._flag)
         return self._hash()
 
+    def _host(self):
+        """exchange="auto": the implementation behind commit_host (collective on first use)"""
+        if self._host_impl is None:
+            self._host_impl = ShardedCommit(self.ctx, self.plan, self.rank, self.dist, self.torch, exchange="stream")
+        return self._host_impl
+
+    def host_columns(self) -> List[int]:
+        """Global indices of the columns this rank passes to commit_host, in order (collective on first use with exchange="auto": the
+        streamed plan deals columns cyclically, the other plans use the contiguous ShardPlan.col_range)."""
+        impl = self._host() if self._auto else self
+        if impl.exchange == "stream":
+            return self.plan.stream_columns(self.rank)
+        return list(range(*self.plan.col_range(self.rank)))
+
     def _hash(self) -> np.ndarray:
         p, lib, h, torch = self.plan, self.ctx.lib, self.ctx.handle, self.torch
         t0 = time.perf_counter()
         self._check(lib.gl_dev_merkle(h, self.leaves_ptr, p.rows_per_rank, p.n_cols, p.leaf_pitch, p.local_cap_height,
                                       self.digests.data_ptr(), self.cap_local.ctypes.data))
         self._merkle_call_ms = (time.perf_counter() - t0) * 1e3
+        return self._gather_cap()
+
+    def _gather_cap(self) -> np.ndarray:
+        torch = self.torch
         with torch.cuda.stream(self._stream):
             self.cap_dev.copy_(torch.from_numpy(self.cap_local.view(np.int64)))
             self.dist.all_gather_into_tensor(self.cap_all, self.cap_dev)

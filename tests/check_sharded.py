@@ -48,13 +48,24 @@ def main():
         plan = ShardPlan(cols, log_n, r, h, world)
         c0, c1 = plan.col_range(rank)
         d = torch.from_numpy(x[c0:c1].view(np.int64).copy()).to(dev)
-        for mode in ("coset", "p2p", "nccl"):
-            if mode == "coset" and world > (1 << r):
+        for mode in os.environ.get("GL_CHECK_MODES", "coset,stream,p2p,nccl,auto").split(","):
+            if mode in ("coset", "stream") and world > (1 << r):
                 continue
             sc = ShardedCommit(ctx, plan, rank, dist, torch, exchange=mode)
-            assert sc.exchange == mode, (sc.exchange, mode)
-            cap = sc.commit(d).reshape(-1, 4)
-            cap2 = sc.commit_host(torch.from_numpy(x[c0:c1].view(np.int64).copy()).pin_memory()).reshape(-1, 4)   # host-column path; buffers reused
+            if mode != "auto":
+                assert sc.exchange == mode, (sc.exchange, mode)
+            idx = sc.host_columns()          # the streamed plan deals the host columns cyclically (ShardPlan.stream_columns)
+            host = torch.from_numpy(x[idx].view(np.int64).copy()).pin_memory()
+            if mode == "stream":             # host columns only; run it three times on the same buffers (epochs / tickets)
+                cap = sc.commit_host(host).reshape(-1, 4).copy()
+                sc.commit_host(host)
+            else:
+                cap = sc.commit(d).reshape(-1, 4)
+            cap2 = sc.commit_host(host).reshape(-1, 4)   # host-column path; buffers reused
+            if mode == "auto":
+                if rank == 0:
+                    print(f"auto: device plan {sc.exchange}, host plan {sc._host().exchange}", flush=True)
+                sc.digests = sc._host().digests
             dig = sc.digests.cpu().numpy().view(np.uint64)[:plan.digests_per_rank() * 4].reshape(-1, 4)
             good = np.array_equal(cap, ref["cap"]) and np.array_equal(cap2, ref["cap"])
             if gold is None:
@@ -68,7 +79,7 @@ def main():
                 import hashlib
                 good = good and hashlib.sha256(b"".join(parts)).hexdigest() == gold["sha256_digests"]
                 # this rank's leaf rows = whole cap subtrees: sha256 per subtree against the oracle's leaves
-                if sc._peer_ptrs is not None or hasattr(sc, "leaves"):
+                if mode != "auto" and (sc._peer_ptrs is not None or hasattr(sc, "leaves")):
                     per = (1 << h) // world
                     sub_rows = plan.rows_per_rank // per
                     lv = np.zeros(plan.rows_per_rank * plan.leaf_pitch, dtype=np.uint64)

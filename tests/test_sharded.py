@@ -189,3 +189,100 @@ def test_coset_plan_over_gloo_world2(shape):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---- streamed coset plan (gl_commit_coset_stream): the cyclic column deal, host logic on CPU + gloo at world_size 2 ----------------------
+def test_stream_columns_partition_and_match_the_library():
+    """every column is dealt to exactly one rank, wave w covers columns [w*G*gw, (w+1)*G*gw) left to right (what the sponge needs), and the
+    C library derives the same wave count / per-rank column count from the same plan (no GPU involved)"""
+    import ctypes
+    from plonky25_b200 import _lib as L
+    lib = L.load()
+    for (cols, log_n, r, h, world) in [(135, 20, 3, 4, 8), (135, 20, 3, 4, 4), (135, 16, 3, 4, 2), (256, 22, 1, 4, 2), (19, 5, 2, 2, 4), (9, 5, 1, 1, 2),
+                                       (9, 4, 3, 3, 8)]:
+        p = ShardPlan(cols, log_n, r, h, world)
+        gw, W = p.stream_group_width(), p.stream_waves()
+        assert gw in (4, 8)
+        dealt = [p.stream_columns(k) for k in range(world)]
+        assert sorted(sum(dealt, [])) == list(range(cols))
+        for w in range(W):
+            wave = sorted(c for k in range(world) for c in dealt[k] if w * world * gw <= c < (w + 1) * world * gw)
+            assert wave == list(range(w * world * gw, min(cols, (w + 1) * world * gw)))
+        for k in range(world):
+            assert dealt[k] == sorted(dealt[k]) and all(c // gw % world == k for c in dealt[k])
+            sp = L.StreamPlan(cols, log_n, r, p.local_cap_height, world, k, gw, p.leaf_pitch, 0)
+            ew, sw, nw, no = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint32()
+            assert lib.gl_stream_plan_sizes(ctypes.byref(sp), ctypes.byref(ew), ctypes.byref(sw), ctypes.byref(nw), ctypes.byref(no)) == 0
+            assert (nw.value, no.value) == (W, len(dealt[k]))
+            assert ew.value == W * (gw << log_n) + world * W and sw.value == world * W * (gw << log_n)
+    bad = L.StreamPlan(135, 20, 1, 1, 4, 0, 4, 136, 0)       # 4 ranks > 2 cosets
+    assert lib.gl_stream_plan_sizes(ctypes.byref(bad), None, None, None, None) != 0
+    bad = L.StreamPlan(135, 20, 3, 1, 8, 0, 6, 136, 0)       # group width must be 4 or 8
+    assert lib.gl_stream_plan_sizes(ctypes.byref(bad), None, None, None, None) != 0
+
+
+def _stream_worker(rank, world, port, cols_shape, q):
+    import torch
+    import torch.distributed as dist
+    from oracle_c import OracleC, splitmix_columns
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_cols, log_n, r, h = cols_shape
+        oc = OracleC()
+        oc.set_threads(1)
+        plan = ShardPlan(n_cols, log_n, r, h, world)
+        gw, W = plan.stream_group_width(), plan.stream_waves()
+        x = splitmix_columns(654, n_cols, 1 << log_n)
+        mine = plan.stream_columns(rank)
+        host = x[mine]                                              # what this rank hands to commit_host, in order
+        blocks = coset_blocks_of_rank(plan, rank)
+        leaves = np.zeros((plan.rows_per_rank, plan.leaf_pitch), dtype=np.uint64)
+        absorbed = 0
+        for w in range(W):
+            own = [j for j, c in enumerate(mine) if c // (gw * world) == w]
+            grp = torch.zeros((gw, 1 << log_n), dtype=torch.int64)     # the wave's own group after the iNTT, padded to gw columns
+            for k, j in enumerate(own):
+                grp[k] = torch.from_numpy(oc.ifft(host[j]).view(np.int64))
+            allg = [torch.zeros_like(grp) for _ in range(world)]
+            dist.all_gather(allg, grp)                              # the product pulls the groups over NVLink behind the tickets
+            for peer, gq in enumerate(allg):
+                c0 = gw * (w * world + peer)
+                nc = max(0, min(gw, n_cols - c0))
+                if nc == 0:
+                    continue
+                for b, (_, s) in enumerate(blocks):
+                    leaves[b << log_n:(b + 1) << log_n, c0:c0 + nc] = _coset_leaves(oc, gq.numpy().view(np.uint64)[:nc], log_n, r, s)
+            c1 = min(n_cols, (w + 1) * world * gw)
+            assert absorbed == w * world * gw and c1 > absorbed      # the sponge sees the leaf strictly left to right, 8-column aligned
+            assert absorbed % 8 == 0
+            absorbed = c1
+        ref = oc.commit(x, r, h)
+        r0, r1 = plan.row_range(rank)
+        ok = bool(np.array_equal(leaves[:, :n_cols], ref["leaves"][r0:r1]))
+        dig, cap = oc.merkle_new(np.ascontiguousarray(leaves[:, :n_cols]), plan.local_cap_height)
+        per = (1 << h) // world
+        ok = ok and bool(np.array_equal(cap, ref["cap"][rank * per:(rank + 1) * per]))
+        ok = ok and bool(np.array_equal(dig, ref["digests"][rank * plan.digests_per_rank():(rank + 1) * plan.digests_per_rank()]))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(19, 5, 2, 2), (135, 4, 1, 1)])
+def test_stream_plan_over_gloo_world2(shape):
+    """two ranks, gloo: wave by wave — iNTT of the own column group, exchange of the wave's groups, own cosets into the own leaf range at the
+    group's column offset; the finished leaf range, digest slice and cap slice equal the single commit's (oracle kernels)"""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_stream_worker, args=(k, 2, port, shape, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

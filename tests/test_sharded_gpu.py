@@ -40,6 +40,7 @@ def test_sharded_commit_all_gpus():
     world = 1 << (min(n, 8).bit_length() - 1)
     out = _run(world)
     assert f"shape (16, 135, 3, 4) world {world} p2p: ok" in out and f"shape (16, 135, 3, 4) world {world} coset: ok" in out
+    assert f"shape (16, 135, 3, 4) world {world} stream: ok" in out
 
 
 def test_sharded_commit_two_gpus():
