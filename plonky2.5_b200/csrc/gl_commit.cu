@@ -404,12 +404,17 @@ void launch_pass(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* l
 //   scatter != nullptr (forward only): the last pass stores to the leaf owners (store_mode 2); dst is then only the
 //                         scratch the earlier passes work in.
 void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32_t dst_pitch, uint32_t cols_padded,
-             uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches, const ntt::Scatter* scatter = nullptr) {
+             uint32_t log_n, bool ifft, const CosetTable* pre, int G, uint32_t* launches, const ntt::Scatter* scatter = nullptr,
+             const uint64_t* const* src_list = nullptr) {
+    // src_list (forward, second-generation kernel only): the cols_padded / G column groups are read from separate [N][G] blocks
+    // src_list[cg] (src and src_pitch ignored); the later passes run in place on dst with 8-column tiles when the width allows
+    if (src_list && (ifft || scatter || c->ntt_version < 2 || (G != 4 && G != 8) || log_n < 3 || cols_padded / G > (uint32_t)ntt::MAX_PEERS))
+        GL_THROW(GL_ERR_INVALID, "run_ntt: unsupported multi-source transform");
     const uint64_t* W = get_roots(c, log_n);
     uint64_t n_inv = ifft ? gl::h_inv(((uint64_t)1 << log_n) % gl::P) : 1;
     // the second-generation kernel has an 11-stage form (2048-row tiles of 4 columns): 2^21 and 2^22 then take two passes instead of three
     const bool wide = c->ntt_version >= 2 && (G == 8 || G == 4) && c->ntt_max_a >= 11 && cols_padded % 4 == 0 &&
-                      (log_n + 9) / 10 > (log_n + 10) / 11 && src_pitch % 2 == 0 && dst_pitch % 2 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
+                      (log_n + 9) / 10 > (log_n + 10) / 11 && !src_list && src_pitch % 2 == 0 && dst_pitch % 2 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0;
     auto passes = plan_passes(log_n, wide ? 11 : 10);
     if (passes.empty()) {
         dim3 grid((cols_padded + 63) / 64, 1u << log_n);
@@ -446,6 +451,23 @@ void run_ntt(gl_ctx* c, uint64_t* src, uint32_t src_pitch, uint64_t* dst, uint32
             p.dst = dst; p.dst_pitch = dst_pitch;
         }
         int g = G;
+        if (src_list) {
+            if (first) {
+                p.src_list = 1; p.src = nullptr; p.src_pitch = (uint32_t)G;
+                for (uint32_t k = 0; k < cols_padded / G; k++) {
+                    if ((uintptr_t)src_list[k] % 16) GL_THROW(GL_ERR_INVALID, "run_ntt: misaligned source block");
+                    p.peer[k] = const_cast<uint64_t*>(src_list[k]);
+                }
+            } else if (cols_padded % 8 == 0) {
+                g = 8;
+            }
+            if (p.dst_pitch % 2 || (uintptr_t)p.dst % 16) GL_THROW(GL_ERR_INVALID, "run_ntt: misaligned destination");
+            if (p.a == 11) g = 4;
+            const bool ok = g == 8 ? launch_pass2<8>(c, p, cols_padded, launches) : launch_pass2<4>(c, p, cols_padded, launches);
+            if (!ok) GL_THROW(GL_ERR_INVALID, "run_ntt: pass size %u has no second-generation kernel", p.a);
+            log_blk -= passes[i];
+            continue;
+        }
         if (c->ntt_version >= 2 && (g == 8 || g == 4)) {
             // 128-bit accesses need even pitches and 16-byte aligned bases (true for every buffer this library lays out)
             const bool aligned = p.src_pitch % 2 == 0 && p.dst_pitch % 2 == 0 && ((uintptr_t)p.src % 16 == 0) && ((uintptr_t)p.dst % 16 == 0);
@@ -1271,21 +1293,45 @@ int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64
         }
     // (4) compute stream: own cosets of the wave's groups as they arrive (own group first), then the wave's columns into the leaf sponge
     bool started = false;
+    std::vector<cudaEvent_t> tr;                                          // GL_TRACE=1: per wave {first group ready, NTTs done, absorbed}
+    auto mark = [&]() {
+        if (!c->trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); tr.push_back(e);
+    };
+    // One launch per pass covers all groups of the wave: the first pass reads every group from the block it arrived in (run_ntt's
+    // src_list), the later passes run in place on the wave's adjacent leaf columns with 8-column tiles.  (Per-group launches — 4-column
+    // transforms of 32-byte row segments, 16 small launches per wave at 8 GPUs — measured 0.95 ms per wave against 0.6 for this form.)
+    const bool one_launch = c->ntt_version >= 2 && log_n >= 3 && c->ntt_max_a <= 10;
     for (uint32_t w = 0; w < W; w++) {
+        bool first_in_wave = true;
+        const uint64_t* srcs[ntt::MAX_PEERS] = {};
+        uint32_t n_src = 0;
         for (uint32_t k = 0; k < G; k++) {
             const uint32_t q = (self + k) % G;
             if (!L.has(q, w)) continue;
             CUDA_CHECK(cudaStreamWaitEvent(c->stream, q == self ? c->own_ev[w] : c->pull_ev[(size_t)w * G + q], 0));
+            if (first_in_wave) { mark(); first_in_wave = false; }
             if (!started) { record(c, GL_STAGE_TRANSPOSE); record(c, GL_STAGE_INTT); record(c, GL_STAGE_LDE); started = true; }   // h2d = until the first group is ready
             uint64_t* coeffs = q == self ? own_buf + w * blk : d_stage + ((uint64_t)q * W + w) * blk;
+            srcs[q] = coeffs;                                            // the groups a wave has are q = 0 .. n_src-1 (a prefix)
+            n_src = std::max(n_src, q + 1);
+            if (one_launch) continue;
             for (uint32_t b = 0; b < blocks_per_rank; b++) {
                 const uint32_t s = h_bitrev(first_block + b, rate_bits);   // leaf block b of the batch is LDE coset bitrev_r(b)
                 uint64_t* dst = d_leaves + (uint64_t)b * N * leaf_pitch + (uint64_t)gw * (w * G + q);
                 run_ntt(c, coeffs, gw, dst, leaf_pitch, gw, log_n, false, &tabs[s], (int)gw, &c->launches[GL_STAGE_LDE]);
             }
         }
+        if (one_launch)
+            for (uint32_t b = 0; b < blocks_per_rank; b++) {
+                const uint32_t s = h_bitrev(first_block + b, rate_bits);
+                uint64_t* dst = d_leaves + (uint64_t)b * N * leaf_pitch + (uint64_t)gw * w * G;
+                run_ntt(c, nullptr, gw, dst, leaf_pitch, n_src * gw, log_n, false, &tabs[s], (int)gw, &c->launches[GL_STAGE_LDE], nullptr, srcs);
+            }
+        mark();
         const uint32_t c0 = w * G * gw, c1 = std::min(C, (w + 1) * G * gw);
         leaf_absorb(c, d_leaves, rows, C, leaf_pitch, cap_height, c0, c1, c->hash_state.p, d_digests, d_cap, w == 0, w + 1 == W, &c->launches[GL_STAGE_LEAF_HASH]);
+        mark();
     }
     record(c, GL_STAGE_LEAF_HASH);
     record(c, GL_STAGE_TREE);
@@ -1299,6 +1345,21 @@ int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64
     CUDA_CHECK(cudaStreamSynchronize(c->send_stream));                   // (both idle by dependency; the host buffers are only borrowed)
     CUDA_CHECK(cudaStreamSynchronize(c->pull_stream));
     for (int i = 0; i < GL_N_STAGES; i++) CUDA_CHECK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    if (c->trace) {
+        std::string line;
+        char buf[96];
+        for (size_t i = 0; i + 2 < tr.size() + 0 && i / 3 < W; i += 3) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, c->ev[GL_STAGE_H2D], tr[i]); cudaEventElapsedTime(&b, c->ev[GL_STAGE_H2D], tr[i + 1]);
+            cudaEventElapsedTime(&d, c->ev[GL_STAGE_H2D], tr[i + 2]);
+            snprintf(buf, sizeof buf, " w%zu: ready %.2f ntt %.2f absorbed %.2f;", i / 3, a, b, d);
+            line += buf;
+        }
+        float tot = 0;
+        cudaEventElapsedTime(&tot, c->ev[GL_STAGE_H2D], c->ev[GL_N_STAGES]);
+        fprintf(stderr, "[gl trace dev %d] streamed coset plan (ms from call start):%s end %.2f\n", c->device, line.c_str(), tot);
+        for (auto e : tr) cudaEventDestroy(e);
+    }
     if (err) GL_THROW(GL_ERR_CUDA, "a peer did not publish its coefficient group within the time limit (GL_PEER_TIMEOUT_MS)");
     return GL_OK;
     GL_API_END(c)

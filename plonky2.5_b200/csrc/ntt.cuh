@@ -43,6 +43,10 @@ struct PassParams {
     uint64_t* peer[MAX_PEERS];
     uint64_t scatter_row0;
     uint32_t log_rows_per_peer, scatter_col0, scatter_pitch, scatter_ncols;   // padding columns (>= ncols) are not stored
+    // src_list != 0 (second-generation kernel, first pass only): column group cg is read from its OWN block peer[cg] = [N][G] (pitch
+    // src_pitch == G) instead of columns [cg*G, (cg+1)*G) of src — the streamed coset plan evaluates the groups pulled from all peers
+    // in one launch, straight from the separate blocks they arrived in
+    uint32_t src_list;
 };
 
 __device__ __forceinline__ uint32_t ins3(uint32_t q, uint32_t sh, uint32_t e) {

@@ -251,6 +251,7 @@ ntt_pass_kernel(const ntt::PassParams p) {
     // two mappings of the tile onto the threads: 8 rows x 2 columns (radix-8 rounds) or 16 rows x 1 column (radix-16 rounds)
     const uint32_t q8 = tid / G2, c2 = tid % G2, q16 = tid / G, c1 = tid % G;
     const uint32_t col2 = cg * G + 2 * c2, col1 = cg * G + c1;
+    const uint64_t* const src = p.src_list ? p.peer[cg] - (size_t)cg * G : p.src;   // one block per column group, or one matrix
 
     if (NR > 1) {
         if (tid == 0) mbar_init(&wl_bar, 1);
@@ -265,13 +266,13 @@ ntt_pass_kernel(const ntt::PassParams p) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
                 const uint64_t row = row_base | ((uint64_t)insk(q8, SH0, e, 3) << b_lo);
-                v[e] = *reinterpret_cast<const ulonglong2*>(p.src + row * p.src_pitch + col2);
+                v[e] = *reinterpret_cast<const ulonglong2*>(src + row * p.src_pitch + col2);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const uint64_t row = row_base | ((uint64_t)insk(q16, SH0, e, 4) << b_lo);
-                u[e] = p.src[row * p.src_pitch + col1];
+                u[e] = src[row * p.src_pitch + col1];
             }
         }
     }
