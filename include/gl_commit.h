@@ -80,6 +80,9 @@ int gl_commit(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_
  * and gl_tree_prove on it returns exactly MerkleTree::prove(i) (the subtree roots are cap entries, so no path crosses contexts).
  * The shard trees carry no coefficient matrix (gl_tree_read(GL_PART_COEFFS) is refused) and gl_tree_get_lde_values does not
  * apply to them.  All contexts are locked for the duration of the call; status and message are reported through ctxs[0].
+ * With one context per DEVICE and n_ctx <= 2^rate_bits the call runs the streamed coset plan (gl_commit_coset_stream below: column groups
+ * dealt cyclically, per wave copy -> iNTT -> ticket -> peers pull -> own cosets -> leaf sponge, no barrier between the first wave and the
+ * cap); otherwise (contexts sharing a device, more contexts than cosets, GL_MULTI_PLAN=p2p) the column->row shipment described above.
  * Tested bit-exact against the oracle with several contexts on one device and with one device per context (tests/test_gpu_parity.py
  * spreads the contexts over every visible GPU; bench.py --gpus N --single-process times it).                                      */
 int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,
@@ -298,7 +301,7 @@ typedef struct {
     uint32_t cap_height;   /* of the rank's own leaf range (global cap height - log2 n_peers) */
     uint32_t n_peers;      /* G, a power of two <= 2^rate_bits */
     uint32_t self;
-    uint32_t group_width;  /* gw: 4 or 8 */
+    uint32_t group_width;  /* gw: 4 or 8; n_peers * gw must be a multiple of 8 (the sponge rate) */
     uint32_t leaf_pitch;   /* words per device leaf row, multiple of 8, >= round_up(C, 8) */
     uint64_t epoch;
 } gl_stream_plan_t;

@@ -330,19 +330,61 @@ void launch_pass_a(gl_ctx* c, const ntt::PassParams& p, uint32_t threads, size_t
     ntt::ntt_pass_kernel<G, A><<<grid, threads, smem, c->stream>>>(p);
 }
 // second-generation pass (ntt2.cuh): two columns per thread, carry-save butterflies, all-shift radix-16 last round
+#ifndef LEAF_BLOCK
+#define LEAF_BLOCK 128
+#endif
+#define LEAF_BLOCK_PRELOAD LEAF_BLOCK
+// once per device: the shared-memory opt-in of a second-generation pass kernel (the attribute belongs to the function on a device)
 template <int G, int A>
-void launch_pass2_a(gl_ctx* c, const ntt::PassParams& p, uint32_t grid) {
+void prepare_pass2() {
     constexpr size_t smem = ntt2::smem_words<A, G>() * 8;
-    constexpr uint32_t threads = (1u << A) * G / 16;
     if (smem > 48 * 1024) {
-        static std::once_flag once[8];   // per device: the attribute belongs to the function on a device
+        static std::once_flag once[8];
         int dev = 0;
         CUDA_CHECK(cudaGetDevice(&dev));
         cudaError_t e = cudaSuccess;
         std::call_once(once[dev & 7], [&] { e = cudaFuncSetAttribute(ntt2::ntt_pass_kernel<G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         CUDA_CHECK(e);
     }
+}
+template <int G, int A>
+void launch_pass2_a(gl_ctx* c, const ntt::PassParams& p, uint32_t grid) {
+    constexpr size_t smem = ntt2::smem_words<A, G>() * 8;
+    constexpr uint32_t threads = (1u << A) * G / 16;
+    prepare_pass2<G, A>();
     ntt2::ntt_pass_kernel<G, A><<<grid, threads, smem, c->stream>>>(p);
+}
+
+// Loads every kernel the streamed coset plan launches into the current device's context (CUDA loads functions lazily, at their first
+// launch, and a load may have to synchronise the context while the runtime's lock is held).  The plan parks ticket waits on the GPU: a
+// first launch that happens while such a wait spins would block behind it — holding the lock another thread of the process needs to launch
+// the very signal the wait is spinning for (observed with gl_commit_multi on two devices: every wait ran into its time limit).  So nothing
+// may be loaded after the first wait is enqueued.
+template <int G, int A>
+void preload_pass2() {
+    cudaFuncAttributes at;
+    CUDA_CHECK(cudaFuncGetAttributes(&at, ntt2::ntt_pass_kernel<G, A>));
+    prepare_pass2<G, A>();
+    if constexpr (A > 3) preload_pass2<G, A - 1>();
+}
+void preload_stream_kernels() {
+    static std::once_flag once[8];
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    cudaError_t e = cudaSuccess;
+    std::call_once(once[dev & 7], [&] {
+        cudaFuncAttributes at;
+        auto load = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, f); };
+        load((const void*)ntt::transpose_in_kernel);
+        load((const void*)ntt::ntt_tiny_kernel);
+        load((const void*)peersync::signal_kernel);
+        load((const void*)peersync::wait_kernel);
+        load((const void*)merkle::leaf_absorb_kernel<LEAF_BLOCK_PRELOAD>);
+        load((const void*)merkle::tree_level_kernel<128>);
+    });
+    CUDA_CHECK(e);
+    preload_pass2<4, 10>();
+    preload_pass2<8, 10>();
 }
 template <int G>
 bool launch_pass2(gl_ctx* c, ntt::PassParams p, uint32_t cols_padded, uint32_t* launches) {
@@ -1175,6 +1217,7 @@ StreamLayout stream_layout(const gl_stream_plan_t* p) {
     if (p->n_peers == 0 || (p->n_peers & (p->n_peers - 1)) || p->n_peers > (uint32_t)ntt::MAX_PEERS || p->self >= p->n_peers)
         GL_THROW(GL_ERR_INVALID, "bad peer count / rank");
     if (p->n_peers > (1u << p->rate_bits)) GL_THROW(GL_ERR_INVALID, "coset sharding needs n_peers <= 2^rate_bits");
+    if ((p->n_peers * p->group_width) % 8) GL_THROW(GL_ERR_INVALID, "a wave (n_peers * group_width columns) must be a multiple of the sponge rate 8");
     if (p->n_cols <= 4) GL_THROW(GL_ERR_UNSUPPORTED, "leaves of <= 4 elements are not hashed (hash_or_noop): use gl_dev_merkle");
     if (p->log_n + p->rate_bits > 31) GL_THROW(GL_ERR_UNSUPPORTED, "log_n + rate_bits > 31");
     if (p->leaf_pitch % 8 || p->leaf_pitch < round_up(p->n_cols, 8u)) GL_THROW(GL_ERR_INVALID, "leaf_pitch must be a multiple of 8 and >= round_up(n_cols, 8)");
@@ -1202,9 +1245,10 @@ int gl_stream_plan_sizes(const gl_stream_plan_t* plan, uint64_t* exported_words,
     }
 }
 
-int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64_t* const* own_cols, int input_is_coeffs,
-                           uint64_t* const* peer_bufs, uint64_t* d_stage, uint64_t* d_leaves, uint64_t* d_digests, uint64_t* out_cap) {
-    GL_API_BEGIN(c)
+namespace {
+// d_cap: device buffer for the rank's subtree roots (nullptr: the context's scratch)
+void coset_stream_impl(gl_ctx* c, const gl_stream_plan_t* plan, const uint64_t* const* own_cols, int input_is_coeffs, uint64_t* const* peer_bufs,
+                       uint64_t* d_stage, uint64_t* d_leaves, uint64_t* d_digests, uint64_t* d_cap, uint64_t* out_cap) {
     const StreamLayout L = stream_layout(plan);
     if (!peer_bufs || !d_stage || !d_leaves || !d_digests || !out_cap) GL_THROW(GL_ERR_INVALID, "NULL pointer");
     const uint32_t G = L.G, gw = L.gw, W = L.W, self = plan->self, log_n = plan->log_n, rate_bits = plan->rate_bits, C = L.C;
@@ -1220,14 +1264,18 @@ int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64
     const uint32_t cap_height = plan->cap_height, leaf_pitch = plan->leaf_pitch;
     const uint64_t flags_off = (uint64_t)W * blk;
     uint64_t* own_buf = peer_bufs[self];
+    preload_stream_kernels();
     get_roots(c, log_n);
     const auto& tabs = get_lde_tables(c, log_n, rate_bits);
+    for (uint32_t a : plan_passes(log_n, 10)) get_pass_roots(c, a);      // (created with a stream synchronise: not while a wait is parked)
     c->in_stage.ensure(blk * W);
     if (!input_is_coeffs) c->vals.ensure(blk * W);
     c->hash_state.ensure(12 * rows);
-    c->scratch.ensure(std::max<uint64_t>(4ULL << cap_height, 1));      // device cap
     c->sync_err.ensure(1);
-    uint64_t* d_cap = c->scratch.p;
+    if (!d_cap) {
+        c->scratch.ensure(std::max<uint64_t>(4ULL << cap_height, 1));
+        d_cap = c->scratch.p;
+    }
     auto grow = [](std::vector<cudaEvent_t>& v, size_t n) {
         size_t old = v.size();
         if (old >= n) return;
@@ -1364,6 +1412,13 @@ int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64
         for (auto e : tr) cudaEventDestroy(e);
     }
     if (err) GL_THROW(GL_ERR_CUDA, "a peer did not publish its coefficient group within the time limit (GL_PEER_TIMEOUT_MS)");
+}
+}  // namespace
+
+int gl_commit_coset_stream(gl_ctx* c, const gl_stream_plan_t* plan, const uint64_t* const* own_cols, int input_is_coeffs,
+                           uint64_t* const* peer_bufs, uint64_t* d_stage, uint64_t* d_leaves, uint64_t* d_digests, uint64_t* out_cap) {
+    GL_API_BEGIN(c)
+    coset_stream_impl(c, plan, own_cols, input_is_coeffs, peer_bufs, d_stage, d_leaves, d_digests, nullptr, out_cap);
     return GL_OK;
     GL_API_END(c)
 }
@@ -1588,6 +1643,25 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
     const uint64_t N = 1ULL << log_n, R = N << rate_bits, rows_per_rank = R / G;
     const uint32_t leaf_pitch = round_up(n_cols, 8);
     const MultiPlan plan(n_cols, G);
+    // Host columns, as many cosets as contexts or more: the STREAMED coset plan (coset_stream_impl) — per wave every context copies and
+    // inverse-transforms its column group, the others pull it behind a ticket, each evaluates its own cosets and absorbs the wave into the
+    // leaf sponge; the workers never meet between the first and the last barrier.  GL_MULTI_PLAN=p2p keeps the column->row shipment.
+    const char* plan_env = getenv("GL_MULTI_PLAN");
+    // One context per DEVICE only: a ticket wait parks the items queued behind it, and streams of different contexts on one device can share
+    // a hardware queue — the peer's signal could sit behind the very wait it is meant to release.  (With one context per device every
+    // device's queues only ever hold that context's own work, enqueued copy -> iNTT + signal -> waits -> compute, so nothing a peer depends on
+    // is ever behind a wait.)
+    bool distinct_devices = true;
+    for (uint32_t g = 0; g < n_ctx; g++)
+        for (uint32_t q = 0; q < g; q++) distinct_devices = distinct_devices && ctxs[q]->device != ctxs[g]->device;
+    const bool streamed = G <= (1u << rate_bits) && n_cols > 4 && distinct_devices && !(plan_env && !strcmp(plan_env, "p2p"));
+    gl_stream_plan_t sp{};
+    sp.n_cols = n_cols; sp.log_n = log_n; sp.rate_bits = rate_bits; sp.cap_height = local_cap_height; sp.n_peers = G;
+    sp.group_width = (n_cols >= 4 * 8 * G || G == 1) ? 8 : 4; sp.leaf_pitch = leaf_pitch; sp.epoch = 0;
+    uint64_t exported_words = 0, stage_words = 0;
+    uint32_t n_waves = 0;
+    if (streamed && gl_stream_plan_sizes(&sp, &exported_words, &stage_words, &n_waves, nullptr) != GL_OK) return fail0(GL_ERR_INVALID, "bad streamed plan");
+    std::vector<uint64_t*> peer_bufs(G, nullptr);
     std::vector<uint64_t*> peer_leaves(G, nullptr);
     std::vector<std::unique_ptr<Tree>> trees(G);
     std::vector<int> rcs(G, GL_OK);
@@ -1621,7 +1695,19 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
             t->digests.ensure(2 * (rows_per_rank - (1ULL << local_cap_height)) * 4);
             t->d_cap.ensure(4ULL << local_cap_height);
             t->cap.resize(4ULL << local_cap_height);
-            t->coeffs.ensure(N * plan.pitches[g]);   // this rank's coefficient slice [N][pitch_g] (not served by gl_tree_read: has_coeffs stays false)
+            if (streamed) {
+                preload_stream_kernels();            // before the barrier: no context may load a kernel once any device parks a ticket wait
+                get_roots(c, log_n);
+                get_lde_tables(c, log_n, rate_bits);
+                for (uint32_t a : plan_passes(log_n, 10)) get_pass_roots(c, a);
+                // exported buffer: this context's coefficient groups [n_waves][N][gw] + the ticket words, which must read 0 before any peer signals
+                t->coeffs.ensure(exported_words);
+                CUDA_CHECK(cudaMemsetAsync(t->coeffs.p + (exported_words - (uint64_t)G * n_waves), 0, (uint64_t)G * n_waves * 8, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                peer_bufs[g] = t->coeffs.p;
+            } else {
+                t->coeffs.ensure(N * plan.pitches[g]);   // this rank's coefficient slice [N][pitch_g] (not served by gl_tree_read: has_coeffs stays false)
+            }
             for (uint32_t q = 0; q < G; q++) {
                 if (ctxs[q]->device == c->device) continue;
                 int can = 0;
@@ -1637,7 +1723,20 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
         barrier.arrive_and_wait();               // all leaf buffers exist
         bool all_ok = true;
         for (uint32_t q = 0; q < G; q++) all_ok = all_ok && rcs[q] == GL_OK;
-        if (all_ok)
+        if (all_ok && streamed)
+            phase([&] {   // B+C streamed: waves of copy / iNTT / ticket / pull / own cosets / absorb, then the tree above the digests
+                CUDA_CHECK(cudaSetDevice(c->device));
+                gl_stream_plan_t mine = sp;
+                mine.self = g;
+                std::vector<const uint64_t*> own;
+                for (uint32_t w = 0; w < n_waves; w++)
+                    for (uint32_t j = sp.group_width * (w * G + g); j < std::min(n_cols, sp.group_width * (w * G + g + 1)); j++) own.push_back(cols[j]);
+                DevBuf stage;
+                stage.ensure(stage_words);
+                Tree* t = trees[g].get();
+                coset_stream_impl(c, &mine, own.data(), input_is_coeffs, peer_bufs.data(), stage.p, t->leaves.p, t->digests.p, t->d_cap.p, t->cap.data());
+            });
+        if (all_ok && !streamed)
             phase([&] {   // B: iNTT + LDE of the column slice; every coset's rows go to their owners
                 CUDA_CHECK(cudaSetDevice(c->device));
                 const uint32_t n_cosets = 1u << rate_bits;
@@ -1648,7 +1747,7 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
         barrier.arrive_and_wait();               // every rank's shipments have landed (lde_scatter_impl returns after its last copy)
         all_ok = true;
         for (uint32_t q = 0; q < G; q++) all_ok = all_ok && rcs[q] == GL_OK;
-        if (all_ok)
+        if (all_ok && !streamed)
             phase([&] {   // C: hash the own leaf range down to this rank's slice of the cap
                 CUDA_CHECK(cudaSetDevice(c->device));
                 Tree* t = trees[g].get();

@@ -72,7 +72,7 @@ class ShardPlan:
     # ---- streamed coset plan (include/gl_commit.h · gl_commit_coset_stream): columns dealt cyclically in groups of gw, waves of G groups ----
     def stream_group_width(self) -> int:
         """8-column groups when that still leaves >= 4 waves to pipeline (the NTT's preferred tile), else 4"""
-        return 8 if self.n_cols >= 4 * 8 * self.world else 4
+        return 8 if self.n_cols >= 4 * 8 * self.world or self.world == 1 else 4
 
     def stream_waves(self) -> int:
         gw = self.stream_group_width()
