@@ -80,9 +80,10 @@ int gl_commit(gl_ctx* ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_
  * and gl_tree_prove on it returns exactly MerkleTree::prove(i) (the subtree roots are cap entries, so no path crosses contexts).
  * The shard trees carry no coefficient matrix (gl_tree_read(GL_PART_COEFFS) is refused) and gl_tree_get_lde_values does not
  * apply to them.  All contexts are locked for the duration of the call; status and message are reported through ctxs[0].
- * With one context per DEVICE and n_ctx <= 2^rate_bits the call runs the streamed coset plan (gl_commit_coset_stream below: column groups
- * dealt cyclically, per wave copy -> iNTT -> ticket -> peers pull -> own cosets -> leaf sponge, no barrier between the first wave and the
- * cap); otherwise (contexts sharing a device, more contexts than cosets, GL_MULTI_PLAN=p2p) the column->row shipment described above.
+ * With TWO contexts on two devices (and 2 <= 2^rate_bits) the call runs the streamed coset plan (gl_commit_coset_stream below: column
+ * groups dealt cyclically, per wave copy -> iNTT -> ticket -> peer pulls -> own cosets -> leaf sponge, no barrier between the first wave
+ * and the cap); otherwise the column->row shipment described above.  GL_MULTI_PLAN=stream forces the streamed plan for any n_ctx <=
+ * 2^rate_bits with one context per device (slower than the shipment at 8 devices in ONE process), =p2p forbids it.
  * Tested bit-exact against the oracle with several contexts on one device and with one device per context (tests/test_gpu_parity.py
  * spreads the contexts over every visible GPU; bench.py --gpus N --single-process times it).                                      */
 int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* cols, uint32_t n_cols, uint32_t log_n, uint32_t rate_bits,

@@ -1645,7 +1645,7 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
     const MultiPlan plan(n_cols, G);
     // Host columns, as many cosets as contexts or more: the STREAMED coset plan (coset_stream_impl) — per wave every context copies and
     // inverse-transforms its column group, the others pull it behind a ticket, each evaluates its own cosets and absorbs the wave into the
-    // leaf sponge; the workers never meet between the first and the last barrier.  GL_MULTI_PLAN=p2p keeps the column->row shipment.
+    // leaf sponge; the workers never meet between the first and the last barrier.
     const char* plan_env = getenv("GL_MULTI_PLAN");
     // One context per DEVICE only: a ticket wait parks the items queued behind it, and streams of different contexts on one device can share
     // a hardware queue — the peer's signal could sit behind the very wait it is meant to release.  (With one context per device every
@@ -1654,7 +1654,12 @@ int gl_commit_multi(gl_ctx* const* ctxs, uint32_t n_ctx, const uint64_t* const* 
     bool distinct_devices = true;
     for (uint32_t g = 0; g < n_ctx; g++)
         for (uint32_t q = 0; q < g; q++) distinct_devices = distinct_devices && ctxs[q]->device != ctxs[g]->device;
-    const bool streamed = G <= (1u << rate_bits) && n_cols > 4 && distinct_devices && !(plan_env && !strcmp(plan_env, "p2p"));
+    // Measured (host columns, 2^20 x 135): 2 devices 2 350 Melem/s streamed against 2 245 with the shipment plan; 8 devices 6 108 against
+    // 6 575 — the streamed plan enqueues ~250 launches / copies / events per context and call, and eight worker threads of ONE process push
+    // them through the same driver locks (one process per GPU does not pay that: 7 491).  So it is the default for two contexts only;
+    // GL_MULTI_PLAN=stream forces it, GL_MULTI_PLAN=p2p forbids it.
+    const bool want_stream = plan_env ? !strcmp(plan_env, "stream") : n_ctx <= 2;
+    const bool streamed = G <= (1u << rate_bits) && n_cols > 4 && distinct_devices && want_stream;
     gl_stream_plan_t sp{};
     sp.n_cols = n_cols; sp.log_n = log_n; sp.rate_bits = rate_bits; sp.cap_height = local_cap_height; sp.n_peers = G;
     sp.group_width = (n_cols >= 4 * 8 * G || G == 1) ? 8 : 4; sp.leaf_pitch = leaf_pitch; sp.epoch = 0;
