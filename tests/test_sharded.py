@@ -215,6 +215,24 @@ def test_stream_columns_partition_and_match_the_library():
             assert lib.gl_stream_plan_sizes(ctypes.byref(sp), ctypes.byref(ew), ctypes.byref(sw), ctypes.byref(nw), ctypes.byref(no)) == 0
             assert (nw.value, no.value) == (W, len(dealt[k]))
             assert ew.value == W * (gw << log_n) + world * W and sw.value == world * W * (gw << log_n)
+    rng = np.random.default_rng(7)                            # the same arithmetic on 300 random plans
+    for _ in range(300):
+        world = 1 << int(rng.integers(0, 4))
+        r = int(rng.integers(world.bit_length() - 1, 5))
+        log_n = int(rng.integers(1, 24))
+        cols = int(rng.integers(max(world, 5), 600))
+        h = int(rng.integers(world.bit_length() - 1, min(log_n + r, 6) + 1))
+        if h > log_n + r:
+            continue
+        p = ShardPlan(cols, log_n, r, h, world)
+        gw, W = p.stream_group_width(), p.stream_waves()
+        dealt = [p.stream_columns(k) for k in range(world)]
+        assert sorted(sum(dealt, [])) == list(range(cols)) and (world * gw) % 8 == 0
+        for k in range(world):
+            sp = L.StreamPlan(cols, log_n, r, p.local_cap_height, world, k, gw, p.leaf_pitch, 0)
+            nw, no = ctypes.c_uint32(), ctypes.c_uint32()
+            assert lib.gl_stream_plan_sizes(ctypes.byref(sp), None, None, ctypes.byref(nw), ctypes.byref(no)) == 0, (cols, log_n, r, h, world)
+            assert (nw.value, no.value) == (W, len(dealt[k]))
     bad = L.StreamPlan(135, 20, 1, 1, 4, 0, 4, 136, 0)       # 4 ranks > 2 cosets
     assert lib.gl_stream_plan_sizes(ctypes.byref(bad), None, None, None, None) != 0
     bad = L.StreamPlan(135, 20, 3, 1, 8, 0, 6, 136, 0)       # group width must be 4 or 8
