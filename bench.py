@@ -593,7 +593,8 @@ def main():
             h2d = int(hb.item())
         parity["e2e_cap_equals_device_cap"] = bool(np.array_equal(cap, cap_dev))
         e2e_stage_ms, _ = ctx.stage_times()
-        e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        host_plan = "gl_commit" if world == 1 else (state._host_impl.exchange if state._host_impl is not None else state.exchange)
+        e2e = {"value": round(cols * n * a.steps / dt / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "plan": host_plan,
                "stage_ms_last_call_rank0": {k: round(v, 3) for k, v in e2e_stage_ms.items() if v},
                "d2h_bytes_per_step": int(cap.nbytes), "ms_per_step": round(dt / a.steps * 1e3, 3),
                "api": "gl_commit (include/gl_commit.h) with pinned host columns; leaves/digests stay device-resident behind the handle"
