@@ -359,3 +359,69 @@ def test_openings_fri_golden_fixture_python_oracle(golden):
     assert [list(e) for e in fp] == f["fri_final_poly"]
     assert o.fri_proof_of_work(ch, f["pow_bits"]) == f["pow_witness"]
     assert [ch.get_challenge() % (n << f["rate_bits"]) for _ in f["query_indices"]] == f["query_indices"]
+
+
+# ---- the prover-side restatement against a restatement of the VERIFIER (oracle/fri_verifier.py) --------------------------------------
+def _prove_for_verifier(log_n, r, cap_h, arities, pow_bits, n_queries, seed):
+    """oracle-only prover run shaped like plonky2's: two oracles, openings at zeta (all polynomials) and g*zeta (the second oracle's)"""
+    n = 1 << log_n
+    cols_a = [[int(v) for v in c] for c in splitmix_columns(seed, 5, n)]
+    cols_b = [[int(v) for v in c] for c in splitmix_columns(seed + 1, 3, n)]
+    batch_a, batch_b = o.PolynomialBatch.from_values(cols_a, r, cap_h), o.PolynomialBatch.from_values(cols_b, r, cap_h)
+    ch = o.Challenger()
+    ch.observe_cap(batch_a.merkle_tree.cap)
+    ch.observe_cap(batch_b.merkle_tree.cap)
+    zeta = ch.get_extension_challenge()
+    g = o.primitive_root_of_unity(log_n)
+    batches = [(zeta, [(0, i) for i in range(5)] + [(1, i) for i in range(3)]), (o.ext_scale(zeta, g), [(1, i) for i in range(3)])]
+    oracles = [batch_a.polynomials, batch_b.polynomials]
+    opened = [[o.ext_eval_poly_ext([(c, 0) for c in oracles[oi][pi]], z) for (oi, pi) in polys] for z, polys in batches]
+    for vals in opened:                                          # the openings are observed before alpha is drawn
+        for v in vals:
+            ch.observe_extension_element(v)
+    import copy
+    verifier_ch = copy.deepcopy(ch)                              # the verifier reaches the same transcript state on its own
+    alpha = ch.get_extension_challenge()
+    final, _ = o.prove_openings_final_poly(batches, oracles, alpha)
+    lde, vals = o.prove_openings_lde(final, r)
+    trees, final_poly = o.fri_committed_trees(lde, vals, ch, arities, r, cap_h)
+    pow_witness = o.fri_proof_of_work(ch, pow_bits)
+    rounds = o.fri_prover_query_rounds([batch_a.merkle_tree, batch_b.merkle_tree], trees, ch, n_queries, arities, n << r)
+    return dict(batches=batches, opened_values=opened, initial_caps=[batch_a.merkle_tree.cap, batch_b.merkle_tree.cap],
+                commit_caps=[t.cap for t in trees], final_poly=final_poly, pow_witness=pow_witness, query_rounds=rounds,
+                reduction_arity_bits=arities, log_n=log_n, rate_bits=r, pow_bits=pow_bits), verifier_ch
+
+
+@pytest.mark.parametrize("cfg", [(5, 2, 1, [2, 1], 4, 5), (6, 1, 2, [3], 3, 4), (6, 3, 0, [1, 2, 1], 2, 4), (4, 2, 2, [], 3, 3)])
+def test_prover_restatement_passes_the_verifier_restatement(cfg):
+    """What verify_fri_proof enforces holds for the prover restatement's proof: Merkle paths of the opened rows, the first layer =
+    sum_b alpha^(k_b) (F_b(x) - F_b(z_b)) / (x - z_b) from the opened rows, every fold = the coset interpolated and evaluated at beta,
+    the last value = final_poly(x), proof of work, transcript order."""
+    import copy
+    import fri_verifier as fv
+    proof, ch = _prove_for_verifier(*cfg, seed=91)
+    fv.verify_fri_proof(challenger=copy.deepcopy(ch), **proof)
+    # and it is a check: every one of these single-word changes is rejected
+    def tampered(mut):
+        p = copy.deepcopy(proof)
+        mut(p)
+        with pytest.raises(AssertionError):
+            fv.verify_fri_proof(challenger=copy.deepcopy(ch), **p)
+    def bump(e):
+        return ((e[0] + 1) % o.P, e[1])
+    tampered(lambda p: p["opened_values"][0].__setitem__(2, bump(p["opened_values"][0][2])))          # a claimed opening
+    tampered(lambda p: p["opened_values"][1].__setitem__(0, bump(p["opened_values"][1][0])))
+    tampered(lambda p: p["final_poly"].__setitem__(0, bump(p["final_poly"][0])))                        # the final polynomial
+    tampered(lambda p: p.__setitem__("pow_witness", p["pow_witness"] + 1))                              # transcript / proof of work
+    if cfg[3]:
+        def step_eval(p):
+            ev = list(p["query_rounds"][0]["steps"][0]["evals"])
+            ev[0] = bump(ev[0])
+            p["query_rounds"][0]["steps"][0]["evals"] = ev
+        tampered(step_eval)                                                                            # a commit-phase evaluation
+    def leaf_word(p):
+        row, path = p["query_rounds"][1]["initial_trees_proof"][0]
+        row = list(row)
+        row[0] = (row[0] + 1) % o.P
+        p["query_rounds"][1]["initial_trees_proof"][0] = (row, path)
+    tampered(leaf_word)                                                                                # an opened leaf row
