@@ -588,7 +588,12 @@ def ext_eval_poly_ext(coeffs: Sequence[Ext], x: Ext) -> Ext:
 
 def prove_openings_final_poly(batches, oracles, alpha: Ext):
     """batches: [(point: Ext, [(oracle_index, polynomial_index), ...])]; oracles: lists of coefficient vectors per oracle.
-    Returns (final_poly coefficients [N], the per-batch quotients)."""
+    Returns (final_poly coefficients [N], the per-batch quotients).
+    Memory note (parity unpinned): early-2022 plonky2 multiplied final_poly by X here (`coeffs.insert(0, ZERO)`, PR #436) and its
+    verifier multiplied fri_combine_initial's sum by subgroup_x; the batch-structured code this restates pads each quotient back to a
+    power of two instead (`quotient.coeffs.push(ZERO)`) and has no such factor on either side.  oracle/fri_verifier.py mirrors that
+    choice, so prover and verifier restatements agree with each other; if the pinned commit did carry the factor, both (and
+    csrc/openings.cuh) would need the same one-line shift."""
     rf = ReducingFactor(alpha)
     final: List[Ext] = []
     quotients = []
