@@ -339,11 +339,11 @@ template <int G, int A>
 void prepare_pass2() {
     constexpr size_t smem = ntt2::smem_words<A, G>() * 8;
     if (smem > 48 * 1024) {
-        static std::once_flag once[8];
+        static std::once_flag once[64];
         int dev = 0;
         CUDA_CHECK(cudaGetDevice(&dev));
         cudaError_t e = cudaSuccess;
-        std::call_once(once[dev & 7], [&] { e = cudaFuncSetAttribute(ntt2::ntt_pass_kernel<G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        std::call_once(once[dev & 63], [&] { e = cudaFuncSetAttribute(ntt2::ntt_pass_kernel<G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         CUDA_CHECK(e);
     }
 }
@@ -368,11 +368,11 @@ void preload_pass2() {
     if constexpr (A > 3) preload_pass2<G, A - 1>();
 }
 void preload_stream_kernels() {
-    static std::once_flag once[8];
+    static std::once_flag once[64];
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     cudaError_t e = cudaSuccess;
-    std::call_once(once[dev & 7], [&] {
+    std::call_once(once[dev & 63], [&] {
         cudaFuncAttributes at;
         auto load = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, f); };
         load((const void*)ntt::transpose_in_kernel);
