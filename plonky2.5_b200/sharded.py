@@ -125,7 +125,11 @@ class ShardedCommit:
     while the next coset's NTT runs (copy engines by default, NTT-side remote stores or a copy kernel with
     GL_SCATTER_MODE), so there is no all-to-all, no receive buffer and no repacking; the ranks only meet at a stream-ordered
     1-element all-reduce before hashing.  exchange="nccl": gl_dev_lde + all_to_all_single + gl_dev_repack (the baseline the
-    fused path is measured against, and the collective fallback when peer mapping is unavailable)."""
+    fused path is measured against, and the collective fallback when peer mapping is unavailable).
+    exchange="coset" (what "auto" picks for device-resident columns when world <= 2^rate_bits): the ranks exchange COEFFICIENT blocks and
+    every rank evaluates only its own cosets (gl_dev_intt + gl_dev_lde_own_cosets).  exchange="stream" (what "auto" picks for HOST columns,
+    commit_host only): the coset plan cut into waves and fused with the leaf sponge (gl_commit_coset_stream) — the columns are dealt
+    cyclically, so ask host_columns() which ones this rank supplies."""
 
     def __init__(self, ctx, plan: ShardPlan, rank: int, dist, torch, exchange: str = "auto"):
         self.ctx, self.plan, self.rank, self.dist, self.torch = ctx, plan, rank, dist, torch
